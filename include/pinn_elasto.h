@@ -1,0 +1,157 @@
+/*
+ * pinn_elasto.h -- C ABI of the B200-native PINN-elastodynamics residual/training engine.
+ *
+ * The reference (Raocp/PINN-elastodynamics) has no FFI: its boundary is the Python class surface
+ * (PINN / DeepHPM / DeepElasticWave) whose hot path is a TensorFlow-1 graph.
+ * Each entry point below replaces the `sess.run` of one group of reference graph nodes; the reference
+ * lines it replaces are cited per function (paths relative to the reference root):
+ *     plate = PlateHoleQuarter/train/train.py        semi = ElasticWaveSemiInfinite/ElasticWave.py
+ *     inf   = ElasticWaveInfinite/ElasticWave.py     conf = ElasticWaveConfined/ElasticWave.py
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats.  No torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *   - every `d_*` pointer is DEVICE memory owned by the caller (the Python host allocates it with torch);
+ *     every `h_*` pointer is host memory.  All device work is asynchronous on `stream`.
+ *   - return value: 0 = ok, non-zero = error; pe_last_error() gives the message (thread-local).
+ *   - network parameters live on the device in a PADDED layout (rows of W_l padded to a multiple of 4
+ *     floats so that 128-bit loads are aligned): [W_0 | W_1 | ... | W_L | b_0 | ... | b_L], W_l stored
+ *     row-major (in, out) like the reference (`plate:263`), pad entries are zero and stay zero.
+ *     pe_pack_params / pe_unpack_params convert from/to the reference's compact order, which is also the
+ *     ScipyOptimizerInterface packing (`var_list = weights + biases`, plate:241).
+ *   - a "point set" is a row-major float array [n, ld]: columns 0..2 are (x, y, t) as in the reference's
+ *     Collo/IC/... arrays (plate:45-88), further columns are per-point targets (SRC u,v: semi:52-53).
+ *   - jet streams carried per point: K=5 (value, d/dx, d/dy, d/dt, d2/dt2) for the plate formulation,
+ *     K=4 (value, d/dx, d/dy, d/dt) for the wave formulation, K=1 for primal-only boundary/data terms,
+ *     K=2 (value, d/dt) for the d/dt data terms of the plate pre-training losses.
+ */
+#ifndef PINN_ELASTO_H
+#define PINN_ELASTO_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_MAX_LAYERS 16        /* weight matrices per network */
+#define PE_MAX_TERMS 8          /* loss-term accumulators per model (loss_f_uv, loss_f_s, loss_IC, ...) */
+#define PE_MAX_COLS 8           /* residual columns of one data term */
+#define PE_TILE_POINTS 32       /* points per CTA tile (one warp lane per point) */
+
+/* residual kinds (what the point set contributes to the loss) */
+enum {
+    PE_RES_F5 = 0,       /* plane-stress momentum + constitutive residuals, 5 outputs  (plate:404-439) */
+    PE_RES_F7 = 1,       /* plane-strain first-order system, 7 outputs              (semi:228-272, inf:221-265, conf:304-348) */
+    PE_RES_COLS = 2,     /* selected output columns minus optional targets          (semi:103-107,119-126; conf:131-148; plate:194-198,201-215) */
+    PE_RES_TRACTION = 3, /* hole traction tx, ty with n = -(x,y)/r                   (plate:452-461) */
+    PE_RES_DT = 4        /* d/dt of selected output columns                          (plate:331-345 net_dist_dt, plate:354-355 net_part) */
+};
+
+/* precision / engine selection for the residual kernels */
+enum {
+    PE_ENGINE_SIMT_FP32 = 0,   /* fp32 FFMA kernels: parity anchor, any width */
+    PE_ENGINE_TC_TF32X3 = 1,   /* tcgen05 tensor-core tiles, 3xTF32 split (fp32-parity mode) */
+    PE_ENGINE_TC_TF32 = 2      /* tcgen05 tensor-core tiles, single-pass TF32 (fast mode) */
+};
+
+typedef struct pe_plan pe_plan; /* host-side description of one network: dims, padded layout, launch config */
+
+/* One loss contribution of one point set.  Replaces the graph nodes named by `kind`. */
+typedef struct pe_term_desc {
+    int kind;                    /* PE_RES_* */
+    int n_global;                /* rows of the GLOBAL point set: the mean's denominator (tf.reduce_mean, plate:187);
+                                    with index sharding each rank passes its shard but the global count */
+    int ld;                      /* row stride of the point array in floats (>= 3) */
+    /* material (plate:39-42, semi:35-37) */
+    float E, mu, rho, hole_r;
+    /* input normalisation H = 2(X-lb)/(ub-lb)-1 (inf:191): a0 = x*in_scale + in_shift; identity = {1,1,1},{0,0,0} */
+    float in_scale[3], in_shift[3];
+    /* F5 / F7: accumulate loss_f_uv into term slot term[0] with weight w[0], loss_f_s into term[1] with w[1]
+       (plate:187-191,217; semi:112-118,127).  TRACTION: tx^2+ty^2 into term[0] (plate:192-193).
+       COLS / DT: column c: residual = out[col[c]] (or its d/dt) - (tgt[c] >= 0 ? row[tgt[c]] : 0), into term[c], weight w[c]. */
+    int ncols;
+    int col[PE_MAX_COLS];
+    int tgt[PE_MAX_COLS];
+    int term[PE_MAX_COLS];
+    float w[PE_MAX_COLS];
+    /* hard-BC composite u = P + D*N (plate:382-387): d_aux holds per point the jets of the frozen
+       dist/part nets, layout [n][2][aux_k][5] (D first, then P); aux_k = streams stored (K of this term). 0 = no composite */
+    int aux_k;
+} pe_term_desc;
+
+/* ---------------------------------------------------------------- library */
+int pe_version(void);
+const char *pe_last_error(void);
+
+/* ---------------------------------------------------------------- plan (host only) */
+/* dims = [3, w1, ..., wL-1, O] as the reference's `uv_layers` (plate:885); device = CUDA ordinal or -1 for
+   "no device" (layout queries only; lets the CPU test-suite exercise the host logic).  NULL on error. */
+pe_plan *pe_plan_create(const int *dims, int n_dims, int device);
+void pe_plan_destroy(pe_plan *plan);
+int pe_plan_param_count(const pe_plan *plan);          /* compact count P = sum d_l*d_{l+1} + sum d_{l+1} */
+int pe_plan_param_count_padded(const pe_plan *plan);   /* padded device length (floats) */
+int pe_plan_weight_offset(const pe_plan *plan, int layer);  /* offset of W_l in the padded vector */
+int pe_plan_bias_offset(const pe_plan *plan, int layer);
+int pe_plan_weight_ld(const pe_plan *plan, int layer);      /* padded row stride of W_l */
+/* number of CTAs (= gradient-partial slots) a launch over n points uses, and scratch sizes */
+int pe_plan_slots(const pe_plan *plan, int n_points, int K);
+size_t pe_plan_stash_floats_per_slot(const pe_plan *plan, int K);
+/* compact (reference order, weights then biases; W_l row-major (in,out)) <-> padded, host memory */
+int pe_pack_params(const pe_plan *plan, const float *h_compact, float *h_padded);
+int pe_unpack_params(const pe_plan *plan, const float *h_padded, float *h_compact);
+
+/* ---------------------------------------------------------------- hot path */
+/* Fused forward-jet MLP + residual + MSE partial sums + reverse sweep (weight/bias gradients) over one
+ * point set.  Replaces, per Adam step / L-BFGS evaluation, the reference's
+ *   net_f_sig / net_uv / net_e graph and its tf.gradients replay      (plate:404-439, 358-396)
+ *   data / boundary terms                                              (plate:452-461, semi:103-107)
+ *   reduce_mean(square(.)) partials                                    (plate:187-193)
+ *   and the reverse-mode of all of the above w.r.t. uv weights+biases  (plate:249-250 minimize()).
+ * Slot s in [slot_base, slot_base + pe_plan_slots()) of d_grad_partials ([slots][padded P]) and
+ * d_term_partials ([slots][PE_MAX_TERMS]) is fully overwritten; nothing is accumulated across calls.
+ * d_stash: scratch of pe_plan_slots() * pe_plan_stash_floats_per_slot() floats, private to this launch while it
+ * runs (launches on one stream may share it).
+ * engine: PE_ENGINE_*.  */
+int pe_residual_loss_grad(const pe_plan *plan, const pe_term_desc *term, int K, int engine,
+                          const float *d_points, int n_local, const float *d_aux,
+                          const float *d_params,
+                          float *d_grad_partials, float *d_term_partials, float *d_stash,
+                          int slot_base, void *stream);
+
+/* Deterministic fixed-order sum over slots: d_out[0..Pp) = sum_s partials[s], d_out[Pp..Pp+PE_MAX_TERMS) =
+ * sum_s term partials.  d_out is the buffer a multi-GPU caller all-reduces.  If d_terms_copy is
+ * non-NULL the PE_MAX_TERMS reduced term values are also written there (per-step loss history row). */
+int pe_reduce_partials(const pe_plan *plan, const float *d_grad_partials, const float *d_term_partials,
+                       int n_slots, float *d_out, float *d_terms_copy, void *stream);
+
+/* tf.train.AdamOptimizer update in TF1 form (plate:249-250):
+ *   lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps).
+ * d_step points to TWO device ints {step, ticket}: step counts completed updates (the kernel uses step+1 and
+ * increments it when its last block retires, so the launch can be replayed from a CUDA graph); ticket must be
+ * zero-initialised.  d_grad = first Pp floats of the reduced buffer. */
+int pe_adam_step(const pe_plan *plan, float *d_params, const float *d_grad, float *d_m, float *d_v,
+                 int *d_step, float lr, float beta1, float beta2, float eps, void *stream);
+
+/* pe_reduce_partials + pe_adam_step in one kernel (single-GPU path: no collective in between); also
+ * writes the reduced gradient and terms to d_out. */
+int pe_reduce_adam(const pe_plan *plan, const float *d_grad_partials, const float *d_term_partials,
+                   int n_slots, float *d_out, float *d_terms_copy, float *d_params, float *d_m, float *d_v, int *d_step,
+                   float lr, float beta1, float beta2, float eps, void *stream);
+
+/* Forward-only fields for `predict` (plate:561-570; semi:348-358): d_out[n][8] =
+ * (u, v, s11, s22, s12, e11, e22, e12); formulation PE_RES_F5 or PE_RES_F7 selects the output columns
+ * (F7 nets return cols 0,1,4,5,6).  Composite as in pe_term_desc (aux_k = 4 streams: value,x,y,t). */
+int pe_forward_fields(const pe_plan *plan, int formulation, const float *d_points, int ld, int n,
+                      const float *in_scale, const float *in_shift, const float *d_aux, int aux_k,
+                      const float *d_params, float *d_out, void *stream);
+
+/* Forward-only jets of all outputs: d_out[n][K][O].  Used to pre-compute the frozen dist/part jets of the
+ * plate composite (plate:361-362: the two extra neural_net calls inside net_uv) and by predict_D/predict_P. */
+int pe_forward_jets(const pe_plan *plan, int K, const float *d_points, int ld, int n,
+                    const float *in_scale, const float *in_shift,
+                    const float *d_params, float *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINN_ELASTO_H */

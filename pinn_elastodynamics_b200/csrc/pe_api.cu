@@ -1,0 +1,225 @@
+// C ABI of libpinn_elasto.so (see include/pinn_elasto.h for the contract and the reference lines each
+// entry point replaces).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "pe_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pe_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st);
+int pe_tc_supported(const pe_plan* plan, int K, int engine);
+int pe_tc_slots(const pe_plan* plan, int n_points);
+
+extern "C" int pe_version(void) { return 100; }
+extern "C" const char* pe_last_error(void) { return g_err; }
+
+static int build_layout(PeLayout& lay, const int* dims, int n_dims) {
+    if (n_dims < 3 || n_dims > PE_MAX_LAYERS + 1) { pe_set_error("need 3..%d layer sizes, got %d", PE_MAX_LAYERS + 1, n_dims); return 1; }
+    if (dims[0] != 3) { pe_set_error("input width must be 3 (x, y, t), got %d", dims[0]); return 1; }
+    memset(&lay, 0, sizeof(lay));
+    lay.L = n_dims - 1;
+    for (int i = 0; i < n_dims; ++i) {
+        if (dims[i] < 1 || dims[i] > 512) { pe_set_error("layer width %d out of range", dims[i]); return 1; }
+        lay.d[i] = dims[i];
+        lay.lda[i] = pe_lda(dims[i]);
+    }
+    if (lay.d[lay.L] > PE_UJ) { pe_set_error("output width %d > %d not supported", lay.d[lay.L], PE_UJ); return 1; }
+    int off = 0, compact = 0;
+    for (int l = 0; l < lay.L; ++l) {
+        lay.ldw[l] = pe_round4(lay.d[l + 1]);
+        lay.woff[l] = off;
+        off += lay.d[l] * lay.ldw[l];
+        compact += lay.d[l] * lay.d[l + 1] + lay.d[l + 1];
+    }
+    for (int l = 0; l < lay.L; ++l) {
+        lay.boff[l] = off;
+        off += lay.ldw[l];
+    }
+    lay.total = off + 128;       // slack: vector loads of partial unit groups may run past the last row (never used)
+    lay.compact = compact;
+    lay.maxw = 0;
+    lay.max_lda = lay.lda[0];
+    int rows = 0;
+    for (int l = 1; l <= lay.L; ++l) {
+        if (l < lay.L) {
+            if (lay.d[l] > lay.maxw) lay.maxw = lay.d[l];
+            lay.soff[l] = rows;
+            rows += lay.lda[l];
+        }
+        if (lay.lda[l] > lay.max_lda) lay.max_lda = lay.lda[l];
+    }
+    lay.stash_rows = rows;
+    int mw = lay.maxw > lay.d[lay.L] ? lay.maxw : lay.d[lay.L];
+    lay.groups = (mw + PE_UJ - 1) / PE_UJ;
+    if (lay.groups > 16) { pe_set_error("hidden width %d too large (max %d)", lay.maxw, 16 * PE_UJ); return 1; }
+    return 0;
+}
+
+extern "C" pe_plan* pe_plan_create(const int* dims, int n_dims, int device) {
+    pe_plan* p = new (std::nothrow) pe_plan();
+    if (!p) { pe_set_error("out of memory"); return nullptr; }
+    if (build_layout(p->lay, dims, n_dims)) { delete p; return nullptr; }
+    p->device = device;
+    p->sms = 148;
+    p->smem_optin = 227 * 1024;
+    if (device >= 0) {
+        cudaDeviceProp prop;
+        cudaError_t e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) { pe_set_error("cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e)); delete p; return nullptr; }
+        p->sms = prop.multiProcessorCount;
+        p->smem_optin = (int)prop.sharedMemPerBlockOptin;
+        if (prop.major != 10) { pe_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); delete p; return nullptr; }
+    }
+    return p;
+}
+
+extern "C" void pe_plan_destroy(pe_plan* plan) { delete plan; }
+extern "C" int pe_plan_param_count(const pe_plan* plan) { return plan ? plan->lay.compact : -1; }
+extern "C" int pe_plan_param_count_padded(const pe_plan* plan) { return plan ? plan->lay.total : -1; }
+extern "C" int pe_plan_weight_offset(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.woff[l] : -1; }
+extern "C" int pe_plan_bias_offset(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.boff[l] : -1; }
+extern "C" int pe_plan_weight_ld(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.ldw[l] : -1; }
+
+extern "C" int pe_plan_slots(const pe_plan* plan, int n_points, int K) {
+    if (!plan) return -1;
+    int ntiles = (n_points + PE_P - 1) / PE_P;
+    int cap = plan->sms * pe_simt_ctas_per_sm(plan, K);
+    int s = ntiles < cap ? ntiles : cap;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" size_t pe_plan_stash_floats_per_slot(const pe_plan* plan, int K) {
+    if (!plan) return 0;
+    return (size_t)K * PE_P * plan->lay.stash_rows + 64;
+}
+
+extern "C" int pe_pack_params(const pe_plan* plan, const float* h_compact, float* h_padded) {
+    if (!plan || !h_compact || !h_padded) { pe_set_error("null argument"); return 1; }
+    const PeLayout& lay = plan->lay;
+    memset(h_padded, 0, sizeof(float) * lay.total);
+    int o = 0;
+    for (int l = 0; l < lay.L; ++l)
+        for (int i = 0; i < lay.d[l]; ++i)
+            for (int j = 0; j < lay.d[l + 1]; ++j) h_padded[lay.woff[l] + i * lay.ldw[l] + j] = h_compact[o++];
+    for (int l = 0; l < lay.L; ++l)
+        for (int j = 0; j < lay.d[l + 1]; ++j) h_padded[lay.boff[l] + j] = h_compact[o++];
+    return 0;
+}
+
+extern "C" int pe_unpack_params(const pe_plan* plan, const float* h_padded, float* h_compact) {
+    if (!plan || !h_compact || !h_padded) { pe_set_error("null argument"); return 1; }
+    const PeLayout& lay = plan->lay;
+    int o = 0;
+    for (int l = 0; l < lay.L; ++l)
+        for (int i = 0; i < lay.d[l]; ++i)
+            for (int j = 0; j < lay.d[l + 1]; ++j) h_compact[o++] = h_padded[lay.woff[l] + i * lay.ldw[l] + j];
+    for (int l = 0; l < lay.L; ++l)
+        for (int j = 0; j < lay.d[l + 1]; ++j) h_compact[o++] = h_padded[lay.boff[l] + j];
+    return 0;
+}
+
+static int check_term(const pe_plan* plan, const pe_term_desc* t, int K) {
+    const int O = plan->lay.d[plan->lay.L];
+    if (t->ld < 3) { pe_set_error("point row stride %d < 3", t->ld); return 1; }
+    if (t->n_global < 1) { pe_set_error("n_global must be >= 1"); return 1; }
+    switch (t->kind) {
+        case PE_RES_F5: if (K != 5 || O != 5) { pe_set_error("PE_RES_F5 needs K=5 and 5 outputs (K=%d, O=%d)", K, O); return 1; } break;
+        case PE_RES_F7: if (K != 4 || O != 7) { pe_set_error("PE_RES_F7 needs K=4 and 7 outputs (K=%d, O=%d)", K, O); return 1; } break;
+        case PE_RES_TRACTION: if (K != 1 || O != 5) { pe_set_error("PE_RES_TRACTION needs K=1 and 5 outputs"); return 1; } break;
+        case PE_RES_COLS: if (K != 1) { pe_set_error("PE_RES_COLS needs K=1"); return 1; } break;
+        case PE_RES_DT: if (K != 2) { pe_set_error("PE_RES_DT needs K=2"); return 1; } break;
+        default: pe_set_error("unknown residual kind %d", t->kind); return 1;
+    }
+    if (t->kind == PE_RES_COLS || t->kind == PE_RES_DT) {
+        if (t->ncols < 1 || t->ncols > PE_MAX_COLS) { pe_set_error("ncols %d out of range", t->ncols); return 1; }
+        for (int c = 0; c < t->ncols; ++c) {
+            if (t->col[c] < 0 || t->col[c] >= O) { pe_set_error("column %d out of range", t->col[c]); return 1; }
+            if (t->tgt[c] >= t->ld) { pe_set_error("target column %d >= row stride %d", t->tgt[c], t->ld); return 1; }
+            if (t->term[c] < 0 || t->term[c] >= PE_MAX_TERMS) { pe_set_error("term slot %d out of range", t->term[c]); return 1; }
+        }
+    } else {
+        int nt = (t->kind == PE_RES_TRACTION) ? 1 : 2;
+        for (int c = 0; c < nt; ++c)
+            if (t->term[c] < 0 || t->term[c] >= PE_MAX_TERMS) { pe_set_error("term slot %d out of range", t->term[c]); return 1; }
+    }
+    if (t->aux_k != 0) {
+        if (!(t->kind == PE_RES_F5 && t->aux_k == 5) && !(t->kind == PE_RES_TRACTION && t->aux_k == 1)) {
+            pe_set_error("composite aux_k=%d not valid for kind %d", t->aux_k, t->kind); return 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int pe_residual_loss_grad(const pe_plan* plan, const pe_term_desc* term, int K, int engine,
+                                     const float* d_points, int n_local, const float* d_aux,
+                                     const float* d_params,
+                                     float* d_grad_partials, float* d_term_partials, float* d_stash,
+                                     int slot_base, void* stream) {
+    if (!plan || !term) { pe_set_error("null plan/term"); return 1; }
+    if (plan->device < 0) { pe_set_error("plan was created without a device"); return 1; }
+    if (check_term(plan, term, K)) return 1;
+    if (n_local < 0) { pe_set_error("negative point count"); return 1; }
+    if (term->aux_k && !d_aux) { pe_set_error("composite requested but d_aux is null"); return 1; }
+    PeResidArgs a;
+    a.lay = plan->lay;
+    a.term = *term;
+    a.points = d_points;
+    a.aux = term->aux_k ? d_aux : nullptr;
+    a.params = d_params;
+    a.grad_partials = d_grad_partials;
+    a.term_partials = d_term_partials;
+    a.stash = d_stash;
+    a.n = n_local;
+    a.slot_base = slot_base;
+    a.stash_floats = (int)pe_plan_stash_floats_per_slot(plan, K);
+    a.inv_n = 1.0f / (float)term->n_global;
+    int slots = pe_plan_slots(plan, n_local, K);
+    if (engine == PE_ENGINE_SIMT_FP32) return pe_launch_resid_simt(plan, a, K, slots, (cudaStream_t)stream);
+    if (engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32) {
+        if (!pe_tc_supported(plan, K, engine)) { pe_set_error("tensor-core engine does not support this network/K"); return 1; }
+        return pe_launch_resid_tc(plan, a, K, engine, slots, (cudaStream_t)stream);
+    }
+    pe_set_error("unknown engine %d", engine);
+    return 1;
+}
+
+extern "C" int pe_forward_fields(const pe_plan* plan, int formulation, const float* d_points, int ld, int n,
+                                 const float* in_scale, const float* in_shift, const float* d_aux, int aux_k,
+                                 const float* d_params, float* d_out, void* stream) {
+    if (!plan) { pe_set_error("null plan"); return 1; }
+    if (plan->device < 0) { pe_set_error("plan was created without a device"); return 1; }
+    const int O = plan->lay.d[plan->lay.L];
+    if ((formulation == PE_RES_F5 && O != 5) || (formulation == PE_RES_F7 && O != 7) ||
+        (formulation != PE_RES_F5 && formulation != PE_RES_F7)) { pe_set_error("formulation %d does not match %d outputs", formulation, O); return 1; }
+    if (aux_k && (aux_k != 4 || formulation != PE_RES_F5 || !d_aux)) { pe_set_error("composite fields need aux_k=4, F5 and d_aux"); return 1; }
+    if (n <= 0) return 0;
+    PeFieldsArgs a;
+    a.lay = plan->lay;
+    a.points = d_points; a.aux = d_aux; a.params = d_params; a.out = d_out;
+    a.n = n; a.ld = ld; a.aux_k = aux_k; a.mode = 0; a.formulation = formulation;
+    for (int i = 0; i < 3; ++i) { a.in_scale[i] = in_scale ? in_scale[i] : 1.f; a.in_shift[i] = in_shift ? in_shift[i] : 0.f; }
+    return pe_launch_fields(plan, a, 4, (cudaStream_t)stream);
+}
+
+extern "C" int pe_forward_jets(const pe_plan* plan, int K, const float* d_points, int ld, int n,
+                               const float* in_scale, const float* in_shift,
+                               const float* d_params, float* d_out, void* stream) {
+    if (!plan) { pe_set_error("null plan"); return 1; }
+    if (plan->device < 0) { pe_set_error("plan was created without a device"); return 1; }
+    if (n <= 0) return 0;
+    PeFieldsArgs a;
+    a.lay = plan->lay;
+    a.points = d_points; a.aux = nullptr; a.params = d_params; a.out = d_out;
+    a.n = n; a.ld = ld; a.aux_k = 0; a.mode = 1; a.formulation = 0;
+    for (int i = 0; i < 3; ++i) { a.in_scale[i] = in_scale ? in_scale[i] : 1.f; a.in_shift[i] = in_shift ? in_shift[i] : 0.f; }
+    return pe_launch_fields(plan, a, K, (cudaStream_t)stream);
+}

@@ -1,0 +1,272 @@
+"""Host-side engine: owns device buffers (torch tensors) and drives the C ABI of libpinn_elasto.so.
+
+torch is plumbing only -- device memory, streams and torch.distributed (NCCL) for the one all-reduce of
+`[grad | loss terms]` per evaluation.  All arithmetic of the hot path happens in the
+hand-written sm_100a kernels behind include/pinn_elasto.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Network:
+    """One tanh MLP resident on one GPU in the padded layout of the C ABI."""
+
+    def __init__(self, layers, device=None):
+        self.lib = L.load()
+        self.layers = [int(x) for x in layers]
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise L.PeError('the PINN-elastodynamics engine runs on CUDA devices only (no CPU fallback)')
+        dims = (C.c_int * len(self.layers))(*self.layers)
+        self.plan = self.lib.pe_plan_create(dims, len(self.layers), self.device.index or 0)
+        if not self.plan:
+            raise L.PeError('pe_plan_create: ' + self.lib.pe_last_error().decode())
+        self.P = self.lib.pe_plan_param_count(self.plan)
+        self.Pp = self.lib.pe_plan_param_count_padded(self.plan)
+        z = lambda n, dt=torch.float32: torch.zeros(n, dtype=dt, device=self.device)
+        self.params, self.m, self.v = z(self.Pp), z(self.Pp), z(self.Pp)
+        self.step = z(2, torch.int32)            # {adam step count, ticket}
+
+    def __del__(self):
+        try:
+            if getattr(self, 'plan', None):
+                self.lib.pe_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # ---- compact <-> padded (reference order: weights then biases, plate:241)
+    def pack(self, flat):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.P, (flat.size, self.P)
+        out = np.zeros(self.Pp, np.float32)
+        L.check(self.lib.pe_pack_params(self.plan, flat.ctypes.data, out.ctypes.data), 'pe_pack_params')
+        return out
+
+    def unpack(self, padded):
+        padded = np.ascontiguousarray(padded, dtype=np.float32)
+        out = np.zeros(self.P, np.float32)
+        L.check(self.lib.pe_unpack_params(self.plan, padded.ctypes.data, out.ctypes.data), 'pe_unpack_params')
+        return out
+
+    def set_flat(self, flat):
+        self.params.copy_(torch.from_numpy(self.pack(flat)))
+
+    def get_flat(self):
+        return self.unpack(self.params.cpu().numpy())
+
+    def set_weights(self, Ws, bs):
+        if len(Ws) != len(self.layers) - 1:
+            raise AssertionError('stored model must have the same number of layers')     # plate:299
+        for l, (w, b) in enumerate(zip(Ws, bs)):
+            if tuple(np.shape(w)) != (self.layers[l], self.layers[l + 1]):
+                raise ValueError(f'layer {l}: weight shape {np.shape(w)} != {(self.layers[l], self.layers[l + 1])}')
+        self.set_flat(np.concatenate([np.asarray(w, np.float64).ravel() for w in Ws] +
+                                     [np.asarray(b, np.float64).ravel() for b in bs]))
+
+    def get_weights(self, dtype=np.float32):
+        flat = self.get_flat()
+        Ws, bs, o = [], [], 0
+        for l in range(len(self.layers) - 1):
+            n = self.layers[l] * self.layers[l + 1]
+            Ws.append(flat[o:o + n].reshape(self.layers[l], self.layers[l + 1]).astype(dtype)); o += n
+        for l in range(len(self.layers) - 1):
+            n = self.layers[l + 1]
+            bs.append(flat[o:o + n].reshape(1, n).astype(dtype)); o += n
+        return Ws, bs
+
+    def reset_optimizer(self):
+        self.m.zero_(); self.v.zero_(); self.step.zero_()
+
+    # ---- forward-only entry points
+    def forward_jets(self, points, K, in_scale=None, in_shift=None):
+        """points: cuda float32 [n, ld] -> [n, K, O] (pe_forward_jets)."""
+        n, ld = points.shape
+        O = self.layers[-1]
+        out = torch.empty((n, K, O), dtype=torch.float32, device=self.device)
+        sc = (C.c_float * 3)(*(in_scale if in_scale is not None else (1, 1, 1)))
+        sh = (C.c_float * 3)(*(in_shift if in_shift is not None else (0, 0, 0)))
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.pe_forward_jets(self.plan, K, _ptr(points), ld, n, sc, sh, _ptr(self.params), _ptr(out), C.c_void_p(st)),
+                'pe_forward_jets')
+        return out
+
+    def forward_fields(self, points, formulation, in_scale=None, in_shift=None, aux=None):
+        """points [n, ld] -> [n, 8] = (u, v, s11, s22, s12, e11, e22, e12) (pe_forward_fields)."""
+        n, ld = points.shape
+        out = torch.empty((n, 8), dtype=torch.float32, device=self.device)
+        sc = (C.c_float * 3)(*(in_scale if in_scale is not None else (1, 1, 1)))
+        sh = (C.c_float * 3)(*(in_shift if in_shift is not None else (0, 0, 0)))
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.pe_forward_fields(self.plan, formulation, _ptr(points), ld, n, sc, sh, _ptr(aux), 4 if aux is not None else 0,
+                                           _ptr(self.params), _ptr(out), C.c_void_p(st)), 'pe_forward_fields')
+        return out
+
+
+class Term:
+    """One loss contribution of one point set (one pe_residual_loss_grad launch per evaluation)."""
+
+    def __init__(self, name, kind, K, points, desc, aux=None, enabled=True):
+        self.name, self.kind, self.K = name, kind, K
+        self.points = points                  # local shard, cuda float32 [n_local, ld]
+        self.desc = desc
+        self.aux = aux
+        self.enabled = enabled
+        self.lo, self.hi = 0, points.shape[0]  # active local row range
+        self.slots = 0
+        self.slot_base = 0
+
+
+def shard_range(n, rank, world):
+    """Contiguous index sharding, the reference's chunk arithmetic (semi:300-302)."""
+    return int(rank * n / world), int((rank + 1) * n / world)
+
+
+class LossEngine:
+    """Loss terms + gradient of one trainable network on one rank."""
+
+    def __init__(self, net: Network, engine='simt', group=None):
+        self.net = net
+        self.lib = net.lib
+        self.device = net.device
+        self.engine = L.ENGINES[engine] if isinstance(engine, str) else int(engine)
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if (group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        self.rank = torch.distributed.get_rank(group) if self.world > 1 else 0
+        self.terms = []
+        self.out = torch.zeros(net.Pp + L.PE_MAX_TERMS, dtype=torch.float32, device=self.device)
+        self._built = False
+        self.launches = 0                      # kernels of this library launched so far (bench `gpu_launches`)
+
+    # ---- term construction
+    def make_desc(self, kind, n_global, ld, E=0.0, mu=0.0, rho=0.0, hole_r=0.1, in_scale=(1, 1, 1), in_shift=(0, 0, 0),
+                  cols=(), tgts=(), terms=(0, 1), weights=(1.0, 1.0), aux_k=0):
+        d = L.TermDesc()
+        d.kind, d.n_global, d.ld = kind, int(n_global), int(ld)
+        d.E, d.mu, d.rho, d.hole_r = E, mu, rho, hole_r
+        for i in range(3):
+            d.in_scale[i] = in_scale[i]; d.in_shift[i] = in_shift[i]
+        d.ncols = len(cols)
+        for i in range(L.PE_MAX_COLS):
+            d.col[i] = cols[i] if i < len(cols) else 0
+            d.tgt[i] = tgts[i] if i < len(tgts) else -1
+            d.term[i] = terms[i] if i < len(terms) else 0
+            d.w[i] = weights[i] if i < len(weights) else 0.0
+        d.aux_k = aux_k
+        return d
+
+    def add_term(self, name, kind, K, points_np, **kw):
+        """points_np: GLOBAL host array [N, ld]; this rank keeps rows shard_range(N, rank, world)."""
+        pts = np.ascontiguousarray(points_np, dtype=np.float32)
+        N, ld = pts.shape
+        a, b = shard_range(N, self.rank, self.world)
+        local = torch.from_numpy(pts[a:b].copy()).to(self.device)
+        aux = kw.pop('aux', None)
+        if aux is not None:
+            aux = aux[a:b].contiguous()
+        desc = self.make_desc(kind, N, ld, **kw)
+        t = Term(name, kind, K, local, desc, aux)
+        t.global_n = N
+        t.global_lo = a
+        self.terms.append(t)
+        self._built = False
+        return t
+
+    def set_chunk(self, term, g_lo, g_hi):
+        """Activate GLOBAL rows [g_lo, g_hi) of a term (reference `batch_num` chunking, semi:299-305).
+        The mean is over the chunk's rows; each rank processes its part of the chunk."""
+        if (g_lo, g_hi) == (0, term.global_n):          # whole set: this rank's resident shard
+            term.lo, term.hi = 0, term.points.shape[0]
+            term.desc.n_global = term.global_n
+        else:
+            if self.world > 1:
+                raise L.PeError('batch_num chunking with world_size > 1 is not supported')
+            term.lo, term.hi = g_lo, g_hi
+            term.desc.n_global = g_hi - g_lo
+        self._built = False
+
+    def build(self):
+        base, stash = 0, 1
+        for t in self.terms:
+            n = t.hi - t.lo
+            t.slots = self.lib.pe_plan_slots(self.net.plan, max(n, 1), t.K)
+            t.slot_base = base
+            base += t.slots
+            stash = max(stash, t.slots * self.lib.pe_plan_stash_floats_per_slot(self.net.plan, t.K))
+        self.n_slots = base
+        need = base * self.net.Pp
+        if not hasattr(self, 'gpart') or self.gpart.numel() < need:
+            self.gpart = torch.empty(need, dtype=torch.float32, device=self.device)
+            self.tpart = torch.empty(base * L.PE_MAX_TERMS, dtype=torch.float32, device=self.device)
+        if not hasattr(self, 'stash') or self.stash.numel() < stash:
+            self.stash = torch.empty(stash, dtype=torch.float32, device=self.device)
+        self._built = True
+
+    # ---- evaluation
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_terms(self):
+        if not self._built:
+            self.build()
+        st = self._stream()
+        slots = 0
+        for t in self.terms:
+            if not t.enabled:
+                continue
+            n = t.hi - t.lo
+            pts = t.points[t.lo:t.hi] if (t.lo, t.hi) != (0, t.points.shape[0]) else t.points
+            aux = None if t.aux is None else t.aux[t.lo:t.hi]
+            L.check(self.lib.pe_residual_loss_grad(self.net.plan, C.byref(t.desc), t.K, self.engine,
+                                                   _ptr(pts), n, _ptr(aux), _ptr(self.net.params),
+                                                   _ptr(self.gpart), _ptr(self.tpart), _ptr(self.stash), slots, st),
+                    f'pe_residual_loss_grad[{t.name}]')
+            slots += t.slots
+            self.launches += 1
+        return slots
+
+    def evaluate(self, hist_row=None):
+        """loss terms + full gradient into self.out = [grad (padded) | terms(8)] (all-reduced over ranks)."""
+        slots = self.launch_terms()
+        copy = hist_row if self.world == 1 else None
+        L.check(self.lib.pe_reduce_partials(self.net.plan, _ptr(self.gpart), _ptr(self.tpart), slots, _ptr(self.out), _ptr(copy), self._stream()),
+                'pe_reduce_partials')
+        self.launches += 1
+        if self.world > 1:
+            torch.distributed.all_reduce(self.out, group=self.group)
+            if hist_row is not None:
+                hist_row.copy_(self.out[self.net.Pp:])
+        return self.out
+
+    def adam_step(self, lr, hist_row=None, beta1=0.9, beta2=0.999, eps=1e-8):
+        """One Adam step (TF1 form).  hist_row receives the PRE-update loss terms of this step."""
+        net = self.net
+        if self.world == 1:
+            slots = self.launch_terms()
+            L.check(self.lib.pe_reduce_adam(net.plan, _ptr(self.gpart), _ptr(self.tpart), slots, _ptr(self.out), _ptr(hist_row),
+                                            _ptr(net.params), _ptr(net.m), _ptr(net.v), _ptr(net.step),
+                                            lr, beta1, beta2, eps, self._stream()), 'pe_reduce_adam')
+            self.launches += 1
+        else:
+            self.evaluate(hist_row)
+            L.check(self.lib.pe_adam_step(net.plan, _ptr(net.params), _ptr(self.out), _ptr(net.m), _ptr(net.v), _ptr(net.step),
+                                          lr, beta1, beta2, eps, self._stream()), 'pe_adam_step')
+            self.launches += 1
+
+    def terms_host(self):
+        return self.out[self.net.Pp:].cpu().numpy().astype(np.float64)
+
+    def grad_compact_host(self):
+        return self.net.unpack(self.out[:self.net.Pp].cpu().numpy())

@@ -1,0 +1,403 @@
+"""Drop-in model classes mirroring the reference's Python class surface.
+
+    PINN             PlateHoleQuarter/train/train.py:26-612            (alias PhysicsInformedNN, BASELINE.json)
+    DeepHPM          ElasticWaveInfinite/ElasticWave.py:21-376 (variant='inf')
+                     ElasticWaveSemiInfinite/ElasticWave.py:23-394 (variant='semi', default)
+    DeepElasticWave  ElasticWaveConfined/ElasticWave.py:21-474
+
+Same constructor arguments, method names, return tuples, print formats and error behaviour
+(`load_NN` asserts the layer count, plate:299).  The TF1 graph + session is replaced by
+`LossEngine` (hand-written sm_100a kernels behind include/pinn_elasto.h); parameters live on the GPU
+in fp32.  Semantics kept: losses are recorded AFTER each update (plate:497,502-505) -- obtained for
+free as the pre-update terms of the next step plus one final evaluation; Adam slots persist across
+train() calls (graph-level slots); each train_bfgs call restarts L-BFGS memory; `batch_num` chunk i
+= rows [int(i*N/B), int((i+1)*N/B)) (semi:299-302); only the uv network is trained by train / train_bfgs.
+"""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import LossEngine, Network
+
+
+def xavier_init_lists(layers, rng):
+    """Xavier N(0, 2/(in+out)) truncated at 2 sigma + zero biases (plate:258-274).  The TF1 RNG stream
+    cannot be reproduced; a numpy Generator seeded with the reference's seed 1111 (plate:22) is used."""
+    Ws, bs = [], []
+    for l in range(len(layers) - 1):
+        fi, fo = layers[l], layers[l + 1]
+        w = rng.standard_normal((fi, fo))
+        bad = np.abs(w) > 2.0
+        while bad.any():
+            w[bad] = rng.standard_normal(int(bad.sum()))
+            bad = np.abs(w) > 2.0
+        Ws.append(w * np.sqrt(2.0 / (fi + fo)))
+        bs.append(np.zeros((1, fo)))
+    return Ws, bs
+
+
+def _col(a):
+    return np.asarray(a, dtype=np.float64).reshape(-1, 1)
+
+
+class _Base:
+    """Shared machinery: networks, engine, Adam loop, SciPy L-BFGS-B driver, predict, pickle I/O."""
+
+    formulation = L.RES_F7
+    term_names = ()          # names of loss-term slots, in slot order
+    term_weights = ()        # weight of each slot in the total loss
+    adam_returns = ()        # which histories train() returns (names; 'loss' = weighted total)
+    print_fmt = 'It: %d, Loss: %.3e'
+    bfgs_options = dict(maxiter=1000, maxfun=1000, maxcor=50, maxls=50, ftol=1e-3 * np.finfo(float).eps)
+
+    def _init_common(self, uv_layers, lb, ub, engine, verbose, dtype):
+        self.count = 0
+        self.lb = lb
+        self.ub = ub
+        self.uv_layers = list(uv_layers)
+        self.verbose = verbose
+        self.dtype = dtype
+        self._engine_name = engine
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.uv_net = Network(self.uv_layers, self.device)
+        self.engine = LossEngine(self.uv_net, engine)
+
+    # ---- parameter I/O (plate:258-306)
+    def initialize_NN(self, layers):
+        if not hasattr(self, '_rng'):
+            self._rng = np.random.default_rng(1111)
+        return xavier_init_lists(layers, self._rng)
+
+    def load_NN(self, fileDir, layers):
+        with open(fileDir, 'rb') as f:
+            uv_weights, uv_biases = pickle.load(f)
+        # Stored model must have the same # of layers (plate:299)
+        assert len(layers) == (len(uv_weights) + 1)
+        if self.verbose:
+            for _ in uv_weights:
+                print("Load NN parameters successfully...")
+        return [np.asarray(w) for w in uv_weights], [np.asarray(b) for b in uv_biases]
+
+    def _save(self, net, fileDir, label):
+        Ws, bs = net.get_weights(self.dtype)
+        with open(fileDir, 'wb') as f:
+            pickle.dump([Ws, bs], f)
+        print("Save " + label + "NN parameters successfully...")
+
+    @property
+    def uv_weights(self):
+        return self.uv_net.get_weights(self.dtype)[0]
+
+    @property
+    def uv_biases(self):
+        return self.uv_net.get_weights(self.dtype)[1]
+
+    # ---- loss bookkeeping
+    def _total(self, terms):
+        return float(sum(w * terms[i] for i, w in enumerate(self.term_weights)))
+
+    def _in_affine(self):
+        return (1, 1, 1), (0, 0, 0)
+
+    def _evaluate_terms(self):
+        self.engine.evaluate()
+        return self.engine.terms_host()
+
+    # ---- Adam loop (plate:475-506, semi:290-328, conf:373-408)
+    def _adam_loop(self, iters, learning_rate, chunks):
+        hist_rows = []
+        eng = self.engine
+        for (a, b) in chunks:
+            if a is not None:
+                eng.set_chunk(self._collo_term, a, b)
+            hist = torch.zeros((iters + 1, L.PE_MAX_TERMS), dtype=torch.float32, device=self.device)
+            for it in range(iters):
+                eng.adam_step(learning_rate, hist[it])                 # hist[it] = terms BEFORE update it
+            eng.evaluate(hist[iters])                                  # terms after the last update
+            h = hist.cpu().numpy().astype(np.float64)
+            if self.verbose:                                           # same lines as plate:499-501, printed after the
+                for it in range(0, iters, 10):                         # asynchronous loop has drained (no per-step host sync)
+                    print(self.print_fmt % (it, self._total(h[it + 1])))
+            hist_rows.append(h[1:])                                    # row it+1 = terms after update it
+        H = np.concatenate(hist_rows, 0) if hist_rows else np.zeros((0, L.PE_MAX_TERMS))
+        out = {name: list(H[:, i]) for i, name in enumerate(self.term_names)}
+        out['loss'] = [self._total(r) for r in H]
+        return out
+
+    def _chunks(self, batch_num):
+        N = self._collo_term.global_n
+        return [(int(i * N / batch_num), int((i + 1) * N / batch_num)) for i in range(batch_num)]
+
+    # ---- L-BFGS-B through SciPy, as tf.contrib.opt.ScipyOptimizerInterface does (plate:240-247,522-525)
+    def _bfgs(self, options, callback, engine=None, net=None, total=None):
+        import scipy.optimize
+        engine = engine or self.engine
+        net = net or self.uv_net
+        total = total or self._total
+
+        def fun(x):
+            net.set_flat(x)
+            engine.evaluate()
+            terms = engine.terms_host()
+            g = engine.grad_compact_host().astype(np.float64)
+            f = total(terms)
+            callback(f)                                   # loss_callback fires on every evaluation (plate:463-465)
+            return f, g
+
+        x0 = net.get_flat().astype(np.float64)
+        res = scipy.optimize.minimize(fun, x0, jac=True, method='L-BFGS-B', options=dict(options))
+        net.set_flat(res.x)
+        return res
+
+    def callback(self, loss):
+        self.count = self.count + 1
+        if self.verbose:
+            print('{} th iterations, Loss: {}'.format(self.count, loss))
+
+    # ---- inference (plate:561-570, semi:348-370)
+    def _points_tensor(self, x_star, y_star, t_star):
+        X = np.concatenate([_col(x_star), _col(y_star), _col(t_star)], 1).astype(np.float32)
+        return torch.from_numpy(X).to(self.device)
+
+    def _predict_aux(self, pts):
+        return None
+
+    def predict(self, x_star, y_star, t_star):
+        pts = self._points_tensor(x_star, y_star, t_star)
+        sc, sh = self._in_affine()
+        out = self.uv_net.forward_fields(pts, self.formulation, sc, sh, self._predict_aux(pts)).cpu().numpy().astype(self.dtype)
+        return tuple(out[:, i:i + 1] for i in range(8))
+
+    def probe(self, x_star, y_star, t_star):
+        return self.predict(x_star, y_star, t_star)
+
+
+# ======================================================================================= plate
+class PINN(_Base):
+    """Defected plate, plane stress, 5 outputs, second-order in t (PlateHoleQuarter/train/train.py:26)."""
+
+    formulation = L.RES_F5
+    term_names = ('loss_f_uv', 'loss_f_s', 'loss_HOLE')
+    term_weights = (10.0, 10.0, 10.0)                       # plate:217
+    print_fmt = 'It: %d, Loss: %.6e'                        # plate:501
+    bfgs_options = dict(maxiter=70000, maxfun=70000, maxcor=50, maxls=50, ftol=0.00001 * np.finfo(float).eps)   # plate:243-247
+    pre_options = dict(maxiter=20000, maxfun=20000, maxcor=50, maxls=50, ftol=0.00001 * np.finfo(float).eps)    # plate:223-237
+
+    def __init__(self, Collo, HOLE, IC, LF, RT, UP, LW, DIST, uv_layers, dist_layers, part_layers, lb, ub,
+                 partDir='', distDir='', uvDir='', engine='simt', verbose=True, dtype=np.float64, composite=None):
+        self._init_common(uv_layers, lb, ub, engine, verbose, dtype)
+        self.E, self.mu, self.rho, self.hole_r = 20.0, 0.25, 1.0, 0.1           # plate:39-42
+        A = lambda a: None if a is None else np.asarray(a, dtype=np.float64)
+        self.Collo, self.HOLE, self.IC, self.LF, self.RT, self.UP, self.LW, self.DIST = map(A, (Collo, HOLE, IC, LF, RT, UP, LW, DIST))
+        self.x_c, self.y_c, self.t_c = self.Collo[:, 0:1], self.Collo[:, 1:2], self.Collo[:, 2:3]
+        self.x_HOLE, self.y_HOLE, self.t_HOLE = self.HOLE[:, 0:1], self.HOLE[:, 1:2], self.HOLE[:, 2:3]
+        self.dist_layers, self.part_layers = dist_layers, part_layers
+        # composite u = P + D*N is used when dist/part networks exist (the reference always builds them, plate:96-106);
+        # composite=False gives the plain 5-output net (BASELINE configs 1/2/4: "5x50 mixed-variable net")
+        self.composite = (dist_layers is not None and part_layers is not None) if composite is None else composite
+        if self.composite:
+            self.dist_net = Network(dist_layers, self.device)
+            self.part_net = Network(part_layers, self.device)
+            self.dist_net.set_weights(*(self.initialize_NN(dist_layers) if distDir == '' else self._loading("dist", distDir, dist_layers)))
+            self.part_net.set_weights(*(self.initialize_NN(part_layers) if partDir == '' else self._loading("part", partDir, part_layers)))
+        self.uv_net.set_weights(*(self.initialize_NN(self.uv_layers) if uvDir == '' else self._loading("uv", uvDir, self.uv_layers)))
+        self._setup_terms()
+
+    def _loading(self, what, d, layers):
+        if self.verbose:
+            print("Loading %s NN ..." % what)
+        return self.load_NN(d, layers)
+
+    def _composite_aux(self, pts, K):
+        """[n][2][K][5]: jets of the frozen dist / part nets at the points (plate:361-362)."""
+        D = self.dist_net.forward_jets(pts, K)
+        P = self.part_net.forward_jets(pts, K)
+        return torch.stack([D, P], 1).contiguous()
+
+    def _setup_terms(self):
+        eng = self.engine
+        eng.terms = []
+        mat = dict(E=self.E, mu=self.mu, rho=self.rho, hole_r=self.hole_r)
+        aux_c = aux_h = None
+        if self.composite:
+            aux_c = self._composite_aux(torch.from_numpy(self.Collo[:, :3].astype(np.float32)).to(self.device), 5)
+            aux_h = self._composite_aux(torch.from_numpy(self.HOLE[:, :3].astype(np.float32)).to(self.device), 1)
+        self._collo_term = eng.add_term('Collo', L.RES_F5, 5, self.Collo[:, :3], terms=(0, 1), weights=(10.0, 10.0),
+                                        aux=aux_c, aux_k=5 if self.composite else 0, **mat)
+        self._hole_term = eng.add_term('HOLE', L.RES_TRACTION, 1, self.HOLE[:, :3], terms=(2,), weights=(10.0,),
+                                       aux=aux_h, aux_k=1 if self.composite else 0, **mat)
+
+    def refresh_composite(self):
+        """Re-evaluate the frozen dist/part jets (after train_bfgs_dist / train_bfgs_part changed them)."""
+        if self.composite:
+            self._setup_terms()
+
+    def save_NN(self, fileDir, TYPE=''):
+        net = {'UV': self.uv_net, 'DIST': getattr(self, 'dist_net', None), 'PART': getattr(self, 'part_net', None)}.get(TYPE)
+        if net is None:
+            raise UnboundLocalError("local variable 'uv_weights' referenced before assignment")   # plate:286-289 falls through
+        self._save(net, fileDir, TYPE + ' ')
+
+    def train(self, iter, learning_rate):
+        r = self._adam_loop(iter, learning_rate, [(None, None)])
+        return r['loss_f_uv'], r['loss_f_s'], r['loss_HOLE'], r['loss']
+
+    def train_bfgs(self, options=None):
+        return self._bfgs(options or self.bfgs_options, self.callback)
+
+    def _predict_aux(self, pts):
+        return self._composite_aux(pts, 4) if self.composite else None
+
+    def predict_D(self, x_star, y_star, t_star):
+        out = self.dist_net.forward_jets(self._points_tensor(x_star, y_star, t_star), 1).cpu().numpy().astype(self.dtype)
+        return tuple(out[:, 0, i:i + 1] for i in range(5))
+
+    def predict_P(self, x_star, y_star, t_star):
+        out = self.part_net.forward_jets(self._points_tensor(x_star, y_star, t_star), 1).cpu().numpy().astype(self.dtype)
+        return tuple(out[:, 0, i:i + 1] for i in range(5))
+
+    def getloss(self):
+        t = self._evaluate_terms()
+        vals = {'loss_f_uv': t[0], 'loss_f_s': t[1], 'loss_HOLE': t[2], 'loss': self._total(t)}
+        for k in ('loss_f_uv', 'loss_f_s', 'loss_HOLE', 'loss'):
+            print(k, vals[k])
+        return vals
+
+
+PhysicsInformedNN = PINN       # the name BASELINE.json's north_star uses
+
+
+# ======================================================================================= waves
+class DeepHPM(_Base):
+    """Elastic wave, plane strain, 7 outputs (u,v,ut,vt,s11,s22,s12), first-order system.
+    variant='semi': ElasticWaveSemiInfinite/ElasticWave.py:23 (loss 5,5,2,2,2; semi:127);
+    variant='inf' : ElasticWaveInfinite/ElasticWave.py:21 (normalised inputs inf:191; loss 1,1,1,1, NB unused inf:119)."""
+
+    formulation = L.RES_F7
+    term_names = ('loss_f_uv', 'loss_f_s', 'loss_IC', 'loss_SRC', 'loss_NB')
+
+    def __init__(self, Collo, SRC, IC, UP, uv_layers, lb, ub, ExistModel=0, modelDir=None, variant='semi',
+                 engine='simt', verbose=True, dtype=None):
+        self.variant = variant
+        if dtype is None:
+            dtype = np.float32 if variant == 'inf' else np.float64
+        self._init_common(uv_layers, lb, ub, engine, verbose, dtype)
+        self.E, self.mu, self.rho = 2.5, 0.25, 1.0                         # semi:35-37
+        self.loss_rec = []                                                  # semi:39
+        if variant == 'semi':
+            self.term_weights = (5.0, 5.0, 2.0, 2.0, 2.0)
+            self.bfgs_options = dict(maxiter=1000, maxfun=1000, maxcor=50, maxls=50, ftol=0.001 * np.finfo(float).eps)      # semi:133-137
+        else:
+            self.term_weights = (1.0, 1.0, 1.0, 1.0, 0.0)
+            self.bfgs_options = dict(maxiter=10000, maxfun=10000, maxcor=50, maxls=50, ftol=0.001 * np.finfo(float).eps)    # inf:125-129
+        A = lambda a: np.asarray(a, dtype=np.float64)
+        self.Collo, self.SRC, self.IC, self.UP = map(A, (Collo, SRC, IC, UP))
+        self.x_c, self.y_c, self.t_c = self.Collo[:, 0:1], self.Collo[:, 1:2], self.Collo[:, 2:3]
+        if ExistModel == 0:
+            self.uv_net.set_weights(*self.initialize_NN(self.uv_layers))
+        else:
+            self.uv_net.set_weights(*self.load_NN(modelDir, self.uv_layers))
+        self._setup_terms()
+
+    def _in_affine(self):
+        if self.variant != 'inf':
+            return (1, 1, 1), (0, 0, 0)
+        lb = np.asarray(self.lb, np.float64).ravel(); ub = np.asarray(self.ub, np.float64).ravel()
+        sc = 2.0 / (ub - lb)
+        return tuple(sc), tuple(-2.0 * lb / (ub - lb) - 1.0)
+
+    def _setup_terms(self):
+        eng = self.engine
+        eng.terms = []
+        sc, sh = self._in_affine()
+        w = self.term_weights
+        com = dict(E=self.E, mu=self.mu, rho=self.rho, in_scale=sc, in_shift=sh)
+        self._collo_term = eng.add_term('Collo', L.RES_F7, 4, self.Collo[:, :3], terms=(0, 1), weights=(w[0], w[1]), **com)
+        eng.add_term('IC', L.RES_COLS, 1, self.IC[:, :3], cols=(0, 1, 2, 3), tgts=(-1,) * 4, terms=(2,) * 4, weights=(w[2],) * 4, **com)
+        eng.add_term('SRC', L.RES_COLS, 1, self.SRC[:, :5], cols=(0, 1), tgts=(3, 4), terms=(3, 3), weights=(w[3],) * 2, **com)
+        eng.add_term('UP', L.RES_COLS, 1, self.UP[:, :3], cols=(5, 6), tgts=(-1, -1), terms=(4, 4), weights=(w[4],) * 2, **com)
+
+    def save_NN(self, fileDir):
+        self._save(self.uv_net, fileDir, '')
+
+    def callback(self, loss):
+        self.count = self.count + 1
+        self.loss_rec.append(loss)                                          # semi:287
+        if self.verbose:
+            print('{} th iterations, Loss: {}'.format(self.count, loss))
+
+    def train(self, iter, learning_rate, batch_num):
+        r = self._adam_loop(iter, learning_rate, self._chunks(batch_num))
+        return r['loss_f_uv'], r['loss_f_s'], r['loss_IC'], r['loss_SRC'], r['loss']
+
+    def train_bfgs(self, batch_num, options=None):
+        for (a, b) in self._chunks(batch_num):
+            self.engine.set_chunk(self._collo_term, a, b)
+            self._bfgs(options or self.bfgs_options, self.callback)
+
+    def getloss(self):
+        N = self._collo_term.global_n
+        self.engine.set_chunk(self._collo_term, 0, N)
+        t = self._evaluate_terms()
+        loss = self._total(t)
+        if self.variant == 'inf':
+            return loss, t[0], t[1], t[2], t[3], t[4]                      # inf:376
+        for k, v in (('loss: ', loss), ('loss_f_uv: ', t[0]), ('loss_f_s: ', t[1]), ('loss_IC: ', t[2]), ('loss_SRC: ', t[3]), ('loss_NB: ', t[4])):
+            print(k, v)                                                     # semi:387-392
+
+
+class DeepElasticWave(_Base):
+    """Confined elastic wave, soft BCs (ElasticWaveConfined/ElasticWave.py:21).  The dist/part networks the
+    reference constructs are never used by its net_uv (conf:282-294) and are not built here."""
+
+    formulation = L.RES_F7
+    term_names = ('loss_f_uv', 'loss_f_s', 'loss_SRC', 'loss_IC', 'loss_FIX')
+    term_weights = (5.0, 5.0, 1.0, 1.0, 1.0)                                # conf:156
+    bfgs_options = dict(maxiter=100000, maxfun=100000, maxcor=50, maxls=50, ftol=1 * np.finfo(float).eps)   # conf:162-166
+
+    def __init__(self, Collo, SRC, IC, FIXED, DIST, uv_layers, dist_layers, part_layers, lb, ub,
+                 uvDir='', partDir='', distDir='', engine='simt', verbose=True, dtype=np.float64):
+        self._init_common(uv_layers, lb, ub, engine, verbose, dtype)
+        self.E, self.mu, self.rho = 2.5, 0.25, 1.0
+        A = lambda a: None if a is None else np.asarray(a, dtype=np.float64)
+        self.Collo, self.SRC, self.IC, self.FIXED, self.DIST = map(A, (Collo, SRC, IC, FIXED, DIST))
+        self.x_c, self.y_c, self.t_c = self.Collo[:, 0:1], self.Collo[:, 1:2], self.Collo[:, 2:3]
+        self.dist_layers, self.part_layers = dist_layers, part_layers
+        if uvDir != '':
+            if self.verbose:
+                print("Loading uv NN ...")
+            self.uv_net.set_weights(*self.load_NN(uvDir, self.uv_layers))
+        else:
+            self.uv_net.set_weights(*self.initialize_NN(self.uv_layers))
+        eng = self.engine
+        w = self.term_weights
+        com = dict(E=self.E, mu=self.mu, rho=self.rho)
+        self._collo_term = eng.add_term('Collo', L.RES_F7, 4, self.Collo[:, :3], terms=(0, 1), weights=(w[0], w[1]), **com)
+        eng.add_term('SRC', L.RES_COLS, 1, self.SRC[:, :5], cols=(0, 1), tgts=(3, 4), terms=(2, 2), weights=(w[2],) * 2, **com)
+        eng.add_term('IC', L.RES_COLS, 1, self.IC[:, :3], cols=(0, 1, 2, 3), tgts=(-1,) * 4, terms=(3,) * 4, weights=(w[3],) * 4, **com)
+        eng.add_term('FIXED', L.RES_COLS, 1, self.FIXED[:, :3], cols=(0, 1), tgts=(-1, -1), terms=(4, 4), weights=(w[4],) * 2, **com)
+
+    def save_NN(self, fileDir, TYPE=''):
+        if TYPE != 'UV':
+            raise UnboundLocalError("local variable 'uv_weights' referenced before assignment")
+        self._save(self.uv_net, fileDir, TYPE + ' ')
+
+    def train(self, iter, learning_rate, batch_num):
+        r = self._adam_loop(iter, learning_rate, self._chunks(batch_num))
+        return r['loss_f_uv'], r['loss_f_s'], r['loss']
+
+    def train_bfgs(self, batch_num, options=None):
+        for (a, b) in self._chunks(batch_num):
+            self.engine.set_chunk(self._collo_term, a, b)
+            self._bfgs(options or self.bfgs_options, self.callback)
+
+    def getloss(self):
+        N = self._collo_term.global_n
+        self.engine.set_chunk(self._collo_term, 0, N)
+        t = self._evaluate_terms()
+        for k, v in (('loss_f_uv', t[0]), ('loss_f_s', t[1]), ('loss_SRC', t[2]), ('loss_IC', t[3]), ('loss_FIX', t[4]), ('loss', self._total(t))):
+            print(k, v)

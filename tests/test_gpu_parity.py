@@ -1,0 +1,279 @@
+"""GPU parity tests: CUDA path (through the C ABI / model classes) vs the float64 oracle on identical inputs.
+
+Tolerances (fp32 compute vs float64 oracle; BASELINE.json north_star asks for 1e-5 relative on the loss):
+  loss terms        rel 1e-5 at random-init weights, 2e-4 on trained checkpoints (terms there are ~1e-5 sums
+                    of cancelling O(1) derivative terms, so fp32 rounding of the residual itself is ~1e-4)
+  gradient          max-abs error per W_l / b_l block <= 2e-5 (random init) / 2e-3 (trained) of the block's max
+  fields (predict)  abs 2e-5 * max(1, |field|max)
+  Adam loss curve   rel 1e-5 per step over the 20-step golden curve
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_torch as R
+from tests.util import layers_of, per_layer_grad_err, random_biases, rel_err, unpack_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def pe():
+    assert torch.cuda.is_available()
+    import pinn_elastodynamics_b200 as pe
+    return pe
+
+
+def _plate(pe, Collo, HOLE, layers, Ws, bs, dist=None, part=None, engine='simt'):
+    dl = layers_of(dist[0]) if dist else None
+    pl = layers_of(part[0]) if part else None
+    m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, dl, pl, None, None, verbose=False, engine=engine)
+    if dist:
+        m.dist_net.set_weights(*dist); m.part_net.set_weights(*part); m.refresh_composite()
+    m.uv_net.set_weights(Ws, bs)
+    return m
+
+
+def _check(m, T_ref, names, g_ref, layers, tol_t, tol_g):
+    m.engine.evaluate()
+    t = m.engine.terms_host()
+    g = m.engine.grad_compact_host()
+    for i, nme in enumerate(names):
+        assert t[i] == pytest.approx(T_ref[nme], rel=tol_t), (nme, t[i], T_ref[nme])
+    errs = per_layer_grad_err(g, g_ref, layers)
+    assert max(e for _, e in errs) <= tol_g, errs
+    return t, g
+
+
+@pytest.mark.parametrize('engine', ['simt'])
+def test_f5_plain_5x50_random_init(pe, golden, engine):
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    bs = random_biases(bs, 3)
+    orc = R.Oracle('plate', Ws, bs)
+    sets = {'Collo': g['f5_collo'], 'HOLE': g['f5_hole']}
+    T, loss, gref = orc.loss_and_grad(sets)
+    m = _plate(pe, sets['Collo'], sets['HOLE'], layers, Ws, bs, engine=engine)
+    _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 1e-5, 2e-5)
+
+
+def test_f5_golden_terms_and_grad(pe, golden):
+    """zero-bias Xavier init exactly as stored in the golden file"""
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs)
+    m.engine.evaluate()
+    t = m.engine.terms_host()
+    np.testing.assert_allclose(t[:3], g['f5_terms'][:3], rtol=1e-5)
+    assert m._total(t) == pytest.approx(g['f5_terms'][3], rel=1e-5)
+    errs = per_layer_grad_err(m.engine.grad_compact_host(), g['f5_grad'], layers)
+    assert max(e for _, e in errs) <= 2e-5, errs
+
+
+def test_f5_composite_plate_checkpoint(pe, golden):
+    g = golden('plate_ckpt.npz')
+    uv, di, pa = unpack_golden(g, 'uv'), unpack_golden(g, 'dist'), unpack_golden(g, 'part')
+    layers = layers_of(uv[0])
+    m = _plate(pe, g['collo'], g['hole'], layers, *uv, dist=di, part=pa)
+    m.engine.evaluate()
+    t = m.engine.terms_host()
+    # SURVEY 8(c) known answers: 3.8686e-05 / 2.4435e-05 (float64)
+    np.testing.assert_allclose(t[:3], g['terms'][:3], rtol=2e-4)
+    errs = per_layer_grad_err(m.engine.grad_compact_host(), g['grad'], layers)
+    assert max(e for _, e in errs) <= 2e-3, errs
+    # predict vs oracle composite prediction and (loosely) vs FEM
+    for k in (10, 20, 50):
+        A = g[f'fem{k}']
+        tt = np.full((A.shape[0], 1), k * 0.125)
+        pred = np.concatenate(m.predict(A[:, 0:1], A[:, 1:2], tt), 1)
+        ref = g[f'pred{k}']
+        for c in range(8):
+            assert np.abs(pred[:, c] - ref[:, c]).max() <= 2e-5 * max(1.0, np.abs(ref[:, c]).max()), (k, c)
+        rel_u = np.linalg.norm(pred[:, 0] - A[:, 2]) / np.linalg.norm(A[:, 2])
+        assert rel_u < 0.03
+
+
+def _wave_sets(g, prefix=''):
+    return {'Collo': g[prefix + 'collo'], 'IC': g[prefix + 'ic'], 'UP': g[prefix + 'up'], 'SRC': g[prefix + 'src']}
+
+
+def test_f7_semi_5x50(pe, golden):
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [7]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    Ws[0] = g['f7_W0']
+    sets = _wave_sets(g, 'f7_')
+    m = pe.DeepHPM(sets['Collo'], sets['SRC'], sets['IC'], sets['UP'], layers, None, None, verbose=False)
+    m.uv_net.set_weights(Ws, bs)
+    m.engine.evaluate()
+    t = m.engine.terms_host()
+    np.testing.assert_allclose(t[:5], g['f7_terms'][:5], rtol=1e-5)
+    assert m._total(t) == pytest.approx(g['f7_terms'][5], rel=1e-5)
+    errs = per_layer_grad_err(m.engine.grad_compact_host(), g['f7_grad'], layers)
+    assert max(e for _, e in errs) <= 2e-5, errs
+
+
+def test_f7_semi_checkpoint_8x100(pe, golden):
+    g = golden('semi_ckpt.npz')
+    uv = unpack_golden(g, 'uv')
+    layers = layers_of(uv[0])
+    sets = _wave_sets(g)
+    m = pe.DeepHPM(sets['Collo'], sets['SRC'], sets['IC'], sets['UP'], layers, None, None, verbose=False)
+    m.uv_net.set_weights(*uv)
+    m.engine.evaluate()
+    t = m.engine.terms_host()
+    np.testing.assert_allclose(t[:5], g['terms'][:5], rtol=2e-4)
+    errs = per_layer_grad_err(m.engine.grad_compact_host(), g['grad'], layers)
+    assert max(e for _, e in errs) <= 2e-3, errs
+    A = g['fem8']
+    pred = np.concatenate(m.predict(A[:, 0:1], A[:, 1:2], np.full((A.shape[0], 1), 2.0)), 1)
+    ref = g['pred8']
+    for c in range(8):
+        assert np.abs(pred[:, c] - ref[:, c]).max() <= 2e-5 * max(1.0, np.abs(ref[:, c]).max()), c
+
+
+@pytest.mark.parametrize('variant', ['inf', 'conf'])
+def test_f7_other_variants(pe, variant):
+    """inf: input normalisation + unit weights (inf:191,119); conf: FIX term, weights 5,5,1,1,1 (conf:156). 6x14 net."""
+    rng = np.random.default_rng(11)
+    layers = [3, 14, 14, 14, 7]
+    Ws, bs = R.xavier_params(layers, seed=5)
+    bs = random_biases(bs, 6)
+    lb, ub = np.array([0., 0., 0.]), np.array([30., 30., 20.])
+    sets = {'Collo': rng.uniform(lb, ub, (333, 3)), 'IC': rng.uniform(lb, ub, (45, 3)), 'UP': rng.uniform(lb, ub, (37, 3)),
+            'FIXED': rng.uniform(lb, ub, (65, 3)),
+            'SRC': np.concatenate([rng.uniform(lb, ub, (50, 3)), rng.standard_normal((50, 2)) * 0.1], 1)}
+    orc = R.Oracle(variant, Ws, bs, lb=lb, ub=ub)
+    T, loss, gref = orc.loss_and_grad(sets)
+    if variant == 'inf':
+        m = pe.DeepHPM(sets['Collo'], sets['SRC'], sets['IC'], sets['UP'], layers, lb, ub, variant='inf', verbose=False)
+        names = ('loss_f_uv', 'loss_f_s', 'loss_IC', 'loss_SRC')
+    else:
+        m = pe.DeepElasticWave(sets['Collo'], sets['SRC'], sets['IC'], sets['FIXED'], None, layers, None, None, lb, ub, verbose=False)
+        names = ('loss_f_uv', 'loss_f_s', 'loss_SRC', 'loss_IC', 'loss_FIX')
+    m.uv_net.set_weights(Ws, bs)
+    t, g = _check(m, T, names, gref, layers, 1e-5, 3e-5)
+    assert m._total(t) == pytest.approx(loss, rel=1e-5)
+    x = rng.uniform(lb, ub, (100, 3))
+    pred = m.predict(x[:, 0:1], x[:, 1:2], x[:, 2:3])
+    ref = orc.predict(x[:, 0:1], x[:, 1:2], x[:, 2:3])
+    for a, b in zip(pred, ref):
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize('n', [1, 31, 32, 33, 95, 32 * 301 + 7])
+def test_ragged_and_large_point_counts(pe, n):
+    """tail tiles (n % 32 != 0), fewer points than one tile, more tiles than resident CTAs"""
+    rng = np.random.default_rng(n)
+    layers = [3, 20, 20, 5]
+    Ws, bs = R.xavier_params(layers, seed=9)
+    bs = random_biases(bs, 4)
+    Collo = rng.uniform([0, 0, 0], [.5, .5, 10], (n, 3))
+    HOLE = rng.uniform([0, 0, 0], [.1, .1, 10], (max(1, n // 7), 3))
+    orc = R.Oracle('plate', Ws, bs)
+    T, loss, gref = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
+    m = _plate(pe, Collo, HOLE, layers, Ws, bs)
+    _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 2e-5, 5e-5)
+
+
+def test_bitwise_deterministic(pe, golden):
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    outs = []
+    for _ in range(2):
+        m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs)
+        m.engine.evaluate()
+        outs.append(m.engine.out.cpu().numpy().copy())
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_adam_curve_matches_golden(pe, golden):
+    """20 Adam steps, post-update losses (plate:496-506) vs the float64 oracle curve."""
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs)
+    l_uv, l_s, l_h, loss = m.train(20, 5e-4)
+    C = g['f5_curve']
+    np.testing.assert_allclose(l_uv, C[:, 0], rtol=1e-5)
+    np.testing.assert_allclose(l_s, C[:, 1], rtol=1e-5)
+    np.testing.assert_allclose(l_h, C[:, 2], rtol=1e-5)
+    np.testing.assert_allclose(loss, C[:, 3], rtol=1e-5)
+    assert rel_err(m.uv_net.get_flat(), g['f5_params_after']) <= 1e-5
+    # Adam slots persist across train() calls (TF graph-level slots): continuing = one 20+5 run of the oracle
+    orc = R.Oracle('plate', Ws, bs)
+    rec = orc.train({'Collo': g['f5_collo'], 'HOLE': g['f5_hole']}, 25, 5e-4)
+    more = m.train(5, 5e-4)[3]
+    np.testing.assert_allclose(more, rec['loss'][20:], rtol=2e-5)
+
+
+def test_f7_adam_curve_and_chunking(pe, golden):
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [7]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    Ws[0] = g['f7_W0']
+    sets = _wave_sets(g, 'f7_')
+    m = pe.DeepHPM(sets['Collo'], sets['SRC'], sets['IC'], sets['UP'], layers, None, None, verbose=False)
+    m.uv_net.set_weights(Ws, bs)
+    out = m.train(20, 5e-4, 1)
+    C = g['f7_curve']
+    for i, col in enumerate((0, 1, 2, 3, 5)):
+        np.testing.assert_allclose(out[i], C[:, col], rtol=1e-5)
+    # batch_num chunking (semi:299-326): 3 chunks x 2 iterations vs oracle
+    m2 = pe.DeepHPM(sets['Collo'], sets['SRC'], sets['IC'], sets['UP'], layers, None, None, verbose=False)
+    m2.uv_net.set_weights(Ws, bs)
+    orc = R.Oracle('semi', Ws, bs)
+    rec = orc.train(sets, 2, 5e-4, batch_num=3)
+    out2 = m2.train(2, 5e-4, 3)
+    assert len(out2[4]) == 6
+    np.testing.assert_allclose(out2[4], rec['loss'], rtol=1e-5)
+
+
+def test_lbfgs_matches_scipy_on_oracle(pe, golden):
+    """train_bfgs drives SciPy L-BFGS-B like ScipyOptimizerInterface (plate:240-247): the same driver on the
+    float64 oracle must follow the same loss sequence for the first evaluations."""
+    import scipy.optimize
+    g = golden('synthetic_5x50.npz')
+    layers = [3, 20, 20, 5]
+    Ws, bs = R.xavier_params(layers, seed=21)
+    Collo, HOLE = g['f5_collo'][:200], g['f5_hole'][:30]
+    m = _plate(pe, Collo, HOLE, layers, Ws, bs)
+    seq = []
+    m.callback = lambda loss: seq.append(loss)
+    opts = dict(maxiter=15, maxfun=15, maxcor=50, maxls=50, ftol=1e-5 * np.finfo(float).eps)
+    m.train_bfgs(opts)
+    orc = R.Oracle('plate', Ws, bs)
+    oseq = []
+
+    def fun(x):
+        orc.set_flat_params(x)
+        _, l, gr = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
+        oseq.append(l)
+        return l, gr
+    scipy.optimize.minimize(fun, orc.flat_params(), jac=True, method='L-BFGS-B', options=opts)
+    n = min(len(seq), len(oseq), 8)
+    assert n >= 5
+    np.testing.assert_allclose(seq[:n], oseq[:n], rtol=5e-4)
+    assert seq[-1] < 0.5 * seq[0]
+
+
+def test_checkpoint_roundtrip_and_layer_assert(pe, tmp_path, golden):
+    g = golden('synthetic_5x50.npz')
+    layers = [3, 20, 20, 5]
+    Ws, bs = R.xavier_params(layers, seed=2)
+    m = _plate(pe, g['f5_collo'][:64], g['f5_hole'][:8], layers, Ws, bs)
+    f = str(tmp_path / 'uv.pickle')
+    m.save_NN(f, 'UV')
+    import pickle
+    W2, b2 = pickle.load(open(f, 'rb'))
+    assert [w.shape for w in W2] == [(3, 20), (20, 20), (20, 5)] and b2[0].shape == (1, 20)
+    np.testing.assert_allclose(W2[1], Ws[1], rtol=1e-6)
+    m2 = pe.PINN(g['f5_collo'][:64], g['f5_hole'][:8], None, None, None, None, None, None, layers, None, None, None, None,
+                 uvDir=f, verbose=False)
+    np.testing.assert_array_equal(m2.uv_net.get_flat(), m.uv_net.get_flat())
+    with pytest.raises(AssertionError):
+        pe.PINN(g['f5_collo'][:64], g['f5_hole'][:8], None, None, None, None, None, None, [3, 20, 20, 20, 5], None, None, None, None,
+                uvDir=f, verbose=False)
