@@ -149,6 +149,7 @@ class LossEngine:
         self.out = torch.zeros(net.Pp + L.PE_MAX_TERMS, dtype=torch.float32, device=self.device)
         self._built = False
         self.launches = 0                      # kernels of this library launched so far (bench `gpu_launches`)
+        self.kernel_events = None              # set to a dict name -> [(start, end)] to time each residual kernel with CUDA events
 
     # ---- term construction
     def make_desc(self, kind, n_global, ld, E=0.0, mu=0.0, rho=0.0, hole_r=0.1, in_scale=(1, 1, 1), in_shift=(0, 0, 0),
@@ -229,10 +230,16 @@ class LossEngine:
             n = t.hi - t.lo
             pts = t.points[t.lo:t.hi] if (t.lo, t.hi) != (0, t.points.shape[0]) else t.points
             aux = None if t.aux is None else t.aux[t.lo:t.hi]
+            if self.kernel_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             L.check(self.lib.pe_residual_loss_grad(self.net.plan, C.byref(t.desc), t.K, self.engine,
                                                    _ptr(pts), n, _ptr(aux), _ptr(self.net.params),
                                                    _ptr(self.gpart), _ptr(self.tpart), _ptr(self.stash), slots, st),
                     f'pe_residual_loss_grad[{t.name}]')
+            if self.kernel_events is not None:
+                e1.record()
+                self.kernel_events.setdefault(t.name, []).append((e0, e1))
             slots += t.slots
             self.launches += 1
         return slots

@@ -108,15 +108,30 @@ class _Base:
         return self.engine.terms_host()
 
     # ---- Adam loop (plate:475-506, semi:290-328, conf:373-408)
-    def _adam_loop(self, iters, learning_rate, chunks):
+    def _adam_loop(self, iters, learning_rate, chunks, refeed=False):
+        """refeed=True reproduces the reference's per-iteration host traffic (feed_dict re-upload of every point
+        array on each sess.run, plate:482-497, and the loss scalars fetched back, plate:502-505): every step
+        copies the point sets host->device from pinned memory and reads the loss terms back (bench `e2e`)."""
         hist_rows = []
         eng = self.engine
+        self.h2d_bytes_per_step = self.d2h_bytes_per_step = 0
+        if refeed:
+            pinned = [(t, t.points.cpu().pin_memory()) for t in eng.terms if t.enabled]
+            self.h2d_bytes_per_step = sum(h.numel() * 4 for _, h in pinned)
+            host_row = torch.zeros(L.PE_MAX_TERMS, dtype=torch.float32).pin_memory()
+            self.d2h_bytes_per_step = host_row.numel() * 4
         for (a, b) in chunks:
             if a is not None:
                 eng.set_chunk(self._collo_term, a, b)
             hist = torch.zeros((iters + 1, L.PE_MAX_TERMS), dtype=torch.float32, device=self.device)
             for it in range(iters):
+                if refeed:
+                    for t, h in pinned:
+                        t.points.copy_(h, non_blocking=True)
                 eng.adam_step(learning_rate, hist[it])                 # hist[it] = terms BEFORE update it
+                if refeed:
+                    host_row.copy_(hist[it], non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
             eng.evaluate(hist[iters])                                  # terms after the last update
             h = hist.cpu().numpy().astype(np.float64)
             if self.verbose:                                           # same lines as plate:499-501, printed after the
@@ -242,8 +257,8 @@ class PINN(_Base):
             raise UnboundLocalError("local variable 'uv_weights' referenced before assignment")   # plate:286-289 falls through
         self._save(net, fileDir, TYPE + ' ')
 
-    def train(self, iter, learning_rate):
-        r = self._adam_loop(iter, learning_rate, [(None, None)])
+    def train(self, iter, learning_rate, refeed=False):
+        r = self._adam_loop(iter, learning_rate, [(None, None)], refeed=refeed)
         return r['loss_f_uv'], r['loss_f_s'], r['loss_HOLE'], r['loss']
 
     def train_bfgs(self, options=None):
