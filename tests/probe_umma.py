@@ -1,0 +1,222 @@
+"""Run on the GPU box: pins tcgen05 descriptor / layout conventions with exact integer GEMMs (see csrc/umma_probe.cu).
+Prints PASS/FAIL per hypothesis; tests/test_gpu_umma_probe.py asserts the ones the engine relies on."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, 'pinn_elastodynamics_b200', 'libumma_probe.so')
+SENT = 0x47C35000  # 99999.0f... any finite marker
+
+
+def lib():
+    l = C.CDLL(LIB)
+    l.umma_probe.restype = C.c_int
+    vp = C.c_void_p
+    l.umma_probe.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_uint32, vp]
+    l.umma_probe_error.restype = C.c_char_p
+    return l
+
+
+def idesc(fmt, M, N, a_mn=0, b_mn=0):
+    """fmt: 0=F16 1=BF16 2=TF32 (a and b); fp32 accumulate."""
+    return (1 << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def sdesc(off, lbo, sbo, layout=0):
+    return ((off >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16) | (((sbo >> 4) & 0x3FFF) << 32) | (1 << 46) | (layout << 61)
+
+
+def run(smem, mmas, out_cols, tmem_img=None, tmem_col0=0):
+    """mmas: list of (kind, a_desc, b_desc, idesc, d_col, accum)."""
+    l = lib()
+    smem = np.ascontiguousarray(smem).view(np.uint8)
+    pad = (-smem.size) % 16
+    smem = np.concatenate([smem, np.zeros(pad, np.uint8)])
+    n = len(mmas)
+    arr = lambda vals, t: np.array(vals, dtype=t)
+    a = arr([m[1] for m in mmas], np.uint64); b = arr([m[2] for m in mmas], np.uint64)
+    i = arr([m[3] for m in mmas], np.uint32); d = arr([m[4] for m in mmas], np.uint32)
+    acc = arr([m[5] for m in mmas], np.uint32); k = arr([m[0] for m in mmas], np.uint32)
+    out = np.zeros((128, out_cols), np.uint32)
+    ti = None if tmem_img is None else np.ascontiguousarray(tmem_img, dtype=np.uint32)
+    rc = l.umma_probe(smem.ctypes.data, smem.size, ti.ctypes.data if ti is not None else None, 0 if ti is None else ti.shape[1], tmem_col0,
+                      n, a.ctypes.data, b.ctypes.data, i.ctypes.data, d.ctypes.data, acc.ctypes.data, k.ctypes.data, out_cols, SENT, out.ctypes.data)
+    if rc:
+        raise RuntimeError(l.umma_probe_error().decode())
+    return out.view(np.float32)
+
+
+def bf16_bits(x):
+    return (np.asarray(x, np.float32).view(np.uint32) >> 16).astype(np.uint16)
+
+
+def chunked(mat, elems_per_chunk):
+    """[rows, K] -> [K/epc][rows][epc]: the engine's operand layout (16-byte chunks of the contiguous index, then rows)."""
+    r, k = mat.shape
+    return np.ascontiguousarray(mat.reshape(r, k // elems_per_chunk, elems_per_chunk).transpose(1, 0, 2))
+
+
+def t_kmajor_tf32(swap=False, K=8, N=64):
+    rng = np.random.default_rng(1)
+    A = rng.integers(-3, 4, (128, K)).astype(np.float32)
+    B = rng.integers(-3, 4, (N, K)).astype(np.float32)
+    ia, ib = chunked(A, 4), chunked(B, 4)
+    smem = np.concatenate([ia.ravel(), ib.ravel()])
+    offb = ia.size * 4
+    lbo_a, sbo_a, lbo_b, sbo_b = 128 * 16, 128, N * 16, 128
+    if swap:
+        lbo_a, sbo_a, lbo_b, sbo_b = sbo_a, lbo_a, sbo_b, lbo_b
+    mm = []
+    for s in range(K // 8):
+        mm.append((0, sdesc(s * 2 * 128 * 16, lbo_a, sbo_a), sdesc(offb + s * 2 * N * 16, lbo_b, sbo_b), idesc(2, 128, N), 0, 1 if s else 0))
+    out = run(smem, mm, N)
+    return np.array_equal(out, A @ B.T), out, A @ B.T
+
+
+def t_mnmajor_tf32(M=64, N=64, P=128, swap=False):
+    """dW-like: D[i][j] = sum_p A[p][i] Z[p][j]; both operands stored [chunk][p][4] (unit-contiguous)."""
+    rng = np.random.default_rng(2)
+    A = rng.integers(-3, 4, (P, M)).astype(np.float32)      # [point][unit i]
+    Z = rng.integers(-3, 4, (P, N)).astype(np.float32)
+    ia, iz = chunked(A, 4), chunked(Z, 4)                   # [ic][p][4]
+    smem = np.concatenate([ia.ravel(), iz.ravel()])
+    offz = ia.size * 4
+    sbo, lbo = P * 16, 128                                  # MN-block stride, K(8-point) block stride
+    if swap:
+        sbo, lbo = lbo, sbo
+    mm = []
+    for s in range(P // 8):
+        mm.append((0, sdesc(s * 128, lbo, sbo), sdesc(offz + s * 128, lbo, sbo), idesc(2, M, N, 1, 1), 0, 1 if s else 0))
+    out = run(smem, mm, N)
+    exp = A.T @ Z
+    if M == 64:
+        lanes = np.concatenate([np.arange(16) + 32 * q for q in range(4)])
+        got = out[lanes]
+        other = np.delete(out, lanes, axis=0)
+        untouched = bool((other.view(np.uint32) == SENT).all())
+    else:
+        got, untouched = out, True
+    return np.array_equal(got, exp), untouched, got, exp
+
+
+def t_bf16_ss(K=16, N=64):
+    rng = np.random.default_rng(3)
+    A = rng.integers(-3, 4, (128, K)).astype(np.float32)
+    B = rng.integers(-3, 4, (N, K)).astype(np.float32)
+    ia, ib = chunked(bf16_bits(A), 8), chunked(bf16_bits(B), 8)
+    smem = np.concatenate([ia.ravel().view(np.uint8), ib.ravel().view(np.uint8)])
+    offb = ia.size * 2
+    mm = [(1, sdesc(s * 2 * 128 * 16, 128 * 16, 128), sdesc(offb + s * 2 * N * 16, N * 16, 128), idesc(1, 128, N), 0, 1 if s else 0) for s in range(K // 16)]
+    out = run(smem, mm, N)
+    return np.array_equal(out, A @ B.T), out, A @ B.T
+
+
+def t_bf16_ts(K=16, N=64, mixed=False):
+    """A (bf16) from tensor memory, packed 2 per 32-bit column (element 2c in the low half); B bf16 K-major in smem."""
+    rng = np.random.default_rng(4)
+    A = rng.integers(-3, 4, (128, K)).astype(np.float32)
+    B = rng.integers(-3, 4, (N, K)).astype(np.float32)
+    ab = bf16_bits(A).astype(np.uint32)
+    timg = (ab[:, 0::2] | (ab[:, 1::2] << 16)).astype(np.uint32)           # [128][K/2]
+    ib = chunked(bf16_bits(B), 8)
+    smem = ib.ravel().view(np.uint8)
+    acol = 256
+    mm = [(2, acol + s * 8, sdesc(s * 2 * N * 16, N * 16, 128), idesc(1, 128, N), 0, 1 if s else 0) for s in range(K // 16)]
+    exp = A @ B.T
+    if mixed:   # tf32 SS first, then the bf16 TS product accumulates into the same columns
+        A2 = rng.integers(-3, 4, (128, 8)).astype(np.float32)
+        B2 = rng.integers(-3, 4, (N, 8)).astype(np.float32)
+        ia2, ib2 = chunked(A2, 4), chunked(B2, 4)
+        off2 = smem.size
+        smem = np.concatenate([smem, ia2.ravel().view(np.uint8), ib2.ravel().view(np.uint8)])
+        offb2 = off2 + ia2.size * 4
+        mm = [(0, sdesc(off2, 128 * 16, 128), sdesc(offb2, N * 16, 128), idesc(2, 128, N), 0, 0)] + \
+             [(2, acol + s * 8, sdesc(s * 2 * N * 16, N * 16, 128), idesc(1, 128, N), 0, 1) for s in range(K // 16)]
+        exp = A2 @ B2.T + exp
+    out = run(smem, mm, N, tmem_img=timg, tmem_col0=acol)
+    return np.array_equal(out, exp), out, exp
+
+
+def t_tf32_truncation():
+    """does kind::tf32 truncate or round the low 13 mantissa bits of fp32 operands?  x = 1 + 2^-11 + 2^-12 (just above the
+    tf32 half-ulp): truncation gives 1.0, round-to-nearest gives 1 + 2^-10."""
+    A = np.zeros((128, 8), np.float32); B = np.zeros((64, 8), np.float32)
+    A[:, 0] = 1 + 2.0 ** -11 + 2.0 ** -12
+    B[:, 0] = 1.0
+    ia, ib = chunked(A, 4), chunked(B, 4)
+    smem = np.concatenate([ia.ravel(), ib.ravel()])
+    out = run(smem, [(0, sdesc(0, 2048, 128), sdesc(ia.size * 4, 1024, 128), idesc(2, 128, 64), 0, 0)], 64)
+    return float(out[0, 0])
+
+
+TESTS = [('kmajor tf32 K=8', lambda: t_kmajor_tf32()), ('kmajor tf32 K=8 swapped LBO/SBO', lambda: t_kmajor_tf32(swap=True)),
+         ('kmajor tf32 K=56 N=64', lambda: t_kmajor_tf32(K=56)), ('kmajor tf32 K=56 N=16', lambda: t_kmajor_tf32(K=56, N=16)),
+         ('mnmajor tf32 M=64 N=64 P=128', lambda: t_mnmajor_tf32()), ('mnmajor swapped', lambda: t_mnmajor_tf32(swap=True)),
+         ('mnmajor tf32 M=64 N=56', lambda: t_mnmajor_tf32(N=56)), ('mnmajor tf32 M=128 N=64', lambda: t_mnmajor_tf32(M=128)),
+         ('mnmajor tf32 M=64 N=8', lambda: t_mnmajor_tf32(N=8)),
+         ('bf16 SS K=16', lambda: t_bf16_ss()), ('bf16 SS K=64', lambda: t_bf16_ss(K=64)),
+         ('bf16 TS K=16', lambda: t_bf16_ts()), ('bf16 TS K=64', lambda: t_bf16_ts(K=64)), ('mixed tf32 SS + bf16 TS accumulate', lambda: t_bf16_ts(K=64, mixed=True)),
+         ('tf32 conversion', None)]
+
+
+def map_mn_operand(which, lbo, sbo, offsets, M=64, N=64, layout=0):
+    """Empirically map (byte offset -> (mn, k)) of an MN-major operand: the other operand is a known-good K-major matrix
+    with entry 2^k, the probed operand holds a single 1.0 at `off`."""
+    res = {}
+    for off in offsets:
+        img = np.zeros(16384, np.float32)
+        img[off // 4] = 1.0
+        if which == 'B':
+            A = np.tile(2.0 ** np.arange(8, dtype=np.float32), (128, 1))
+            ia = chunked(A, 4)
+            smem = np.concatenate([ia.ravel(), img])
+            mm = [(0, sdesc(0, 2048, 128), sdesc(ia.size * 4, lbo, sbo, layout), idesc(2, 128, N, 0, 1), 0, 0)]
+            out = run(smem, mm, N)
+            nz = np.argwhere(out[0] != 0).ravel()
+            res[off] = [(int(n), float(np.log2(out[0, n]))) for n in nz]
+        else:
+            B = np.tile(2.0 ** np.arange(8, dtype=np.float32), (N, 1))
+            ib = chunked(B, 4)
+            smem = np.concatenate([ib.ravel(), img])
+            mm = [(0, sdesc(ib.size * 4, lbo, sbo, layout), sdesc(0, N * 16, 128), idesc(2, M, N, 1, 0), 0, 0)]
+            out = run(smem, mm, N)
+            nz = np.argwhere((out[:, 0] != 0) & (out[:, 0].view(np.uint32) != SENT)).ravel()
+            res[off] = [(int(m), float(np.log2(out[m, 0]))) for m in nz]
+    return res
+
+
+
+
+if __name__ == '__main__':
+    import subprocess
+    if len(sys.argv) > 1 and sys.argv[1] == 'map':
+        offs = [0, 4, 8, 12, 16, 32, 48, 64, 96, 112, 128, 144, 160, 256, 272, 384, 512, 1024, 1040, 2048, 2064, 4096, 4112, 8192]
+        np.set_printoptions(linewidth=250)
+        for layout in (0, 6, 4, 2):
+            for which in ('B', 'A'):
+                for (lbo, sbo) in ((4096, 1024), (1024, 4096)):
+                    r = map_mn_operand(which, lbo, sbo, offs, layout=layout)
+                    print('layout', layout, which, 'lbo', lbo, 'sbo', sbo, {k: v for k, v in r.items() if v})
+        sys.exit(0)
+    if len(sys.argv) == 1:            # one process per hypothesis: a faulting descriptor must not take the others down
+        for i in range(len(TESTS)):
+            r = subprocess.run([sys.executable, __file__, str(i)], capture_output=True, text=True, timeout=120)
+            print((r.stdout + r.stderr).strip()[-1500:])
+        sys.exit(0)
+    nm, fn = TESTS[int(sys.argv[1])]
+    try:
+        if fn is None:
+            print('tf32 operand conversion of 1+2^-11+2^-12 ->', t_tf32_truncation(), '(1.0 = truncation, 1.0009766 = round-to-nearest)')
+        else:
+            r = fn()
+            print(('PASS ' if r[0] else 'FAIL ') + nm, *[x for x in r[1:] if isinstance(x, (bool, float))])
+            if not r[0]:
+                got, exp = r[-2], r[-1]
+                np.set_printoptions(linewidth=200)
+                print('   got[0,:8]', got[0, :8], '\n   exp[0,:8]', exp[0, :8], '\n   got[1,:8]', got[1, :8], '\n   exp[1,:8]', exp[1, :8],
+                      '\n   rows matching:', int((got == exp).all(1).sum()), 'of', got.shape[0], ' cols matching:', int((got == exp).all(0).sum()), 'of', got.shape[1])
+    except Exception as e:
+        print('ERROR', nm, e)
