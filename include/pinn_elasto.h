@@ -93,9 +93,12 @@ int pe_plan_param_count_padded(const pe_plan *plan);   /* padded device length (
 int pe_plan_weight_offset(const pe_plan *plan, int layer);  /* offset of W_l in the padded vector */
 int pe_plan_bias_offset(const pe_plan *plan, int layer);
 int pe_plan_weight_ld(const pe_plan *plan, int layer);      /* padded row stride of W_l */
-/* number of CTAs (= gradient-partial slots) a launch over n points uses, and scratch sizes */
-int pe_plan_slots(const pe_plan *plan, int n_points, int K);
-size_t pe_plan_stash_floats_per_slot(const pe_plan *plan, int K);
+/* does `engine` (PE_ENGINE_*) implement residual `kind` with K streams for this network?  The tensor-core engines
+   cover PE_RES_F5 with hidden widths <= 56; the SIMT engine covers everything. */
+int pe_engine_supported(const pe_plan *plan, int kind, int K, int engine);
+/* number of CTAs (= gradient-partial slots) a launch over n points uses, and its scratch size in floats */
+int pe_plan_slots(const pe_plan *plan, int n_points, int K, int engine);
+size_t pe_plan_scratch_floats(const pe_plan *plan, int n_points, int K, int engine);
 /* compact (reference order, weights then biases; W_l row-major (in,out)) <-> padded, host memory */
 int pe_pack_params(const pe_plan *plan, const float *h_compact, float *h_padded);
 int pe_unpack_params(const pe_plan *plan, const float *h_padded, float *h_compact);
@@ -109,8 +112,8 @@ int pe_unpack_params(const pe_plan *plan, const float *h_padded, float *h_compac
  *   and the reverse-mode of all of the above w.r.t. uv weights+biases  (plate:249-250 minimize()).
  * Slot s in [slot_base, slot_base + pe_plan_slots()) of d_grad_partials ([slots][padded P]) and
  * d_term_partials ([slots][PE_MAX_TERMS]) is fully overwritten; nothing is accumulated across calls.
- * d_stash: scratch of pe_plan_slots() * pe_plan_stash_floats_per_slot() floats, private to this launch while it
- * runs (launches on one stream may share it).
+ * d_stash: scratch of pe_plan_scratch_floats() floats, private to this launch while it runs (launches on one
+ * stream may share it): the per-CTA stash of hidden activations (kept L2-resident) + tensor-core operand images.
  * engine: PE_ENGINE_*.  */
 int pe_residual_loss_grad(const pe_plan *plan, const pe_term_desc *term, int K, int engine,
                           const float *d_points, int n_local, const float *d_aux,

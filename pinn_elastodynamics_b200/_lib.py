@@ -48,8 +48,9 @@ SYMBOLS = [
     ('pe_plan_weight_offset', _i, [_vp, _i]),
     ('pe_plan_bias_offset', _i, [_vp, _i]),
     ('pe_plan_weight_ld', _i, [_vp, _i]),
-    ('pe_plan_slots', _i, [_vp, _i, _i]),
-    ('pe_plan_stash_floats_per_slot', C.c_size_t, [_vp, _i]),
+    ('pe_engine_supported', _i, [_vp, _i, _i, _i]),
+    ('pe_plan_slots', _i, [_vp, _i, _i, _i]),
+    ('pe_plan_scratch_floats', C.c_size_t, [_vp, _i, _i, _i]),
     ('pe_pack_params', _i, [_vp, _vp, _vp]),
     ('pe_unpack_params', _i, [_vp, _vp, _vp]),
     ('pe_residual_loss_grad', _i, [_vp, C.POINTER(TermDesc), _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

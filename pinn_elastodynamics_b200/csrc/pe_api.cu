@@ -18,6 +18,8 @@ void pe_set_error(const char* fmt, ...) {
 int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st);
 int pe_tc_supported(const pe_plan* plan, int K, int engine);
 int pe_tc_slots(const pe_plan* plan, int n_points);
+size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
+size_t pe_tc_image_floats(const pe_plan* plan);
 
 extern "C" int pe_version(void) { return 100; }
 extern "C" const char* pe_last_error(void) { return g_err; }
@@ -89,17 +91,31 @@ extern "C" int pe_plan_weight_offset(const pe_plan* plan, int l) { return (plan 
 extern "C" int pe_plan_bias_offset(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.boff[l] : -1; }
 extern "C" int pe_plan_weight_ld(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.ldw[l] : -1; }
 
-extern "C" int pe_plan_slots(const pe_plan* plan, int n_points, int K) {
+static bool is_tc(int engine) { return engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32; }
+
+extern "C" int pe_engine_supported(const pe_plan* plan, int kind, int K, int engine) {
+    if (!plan) return 0;
+    if (engine == PE_ENGINE_SIMT_FP32) return 1;
+    if (is_tc(engine)) return kind == PE_RES_F5 && pe_tc_supported(plan, K, engine);
+    return 0;
+}
+
+extern "C" int pe_plan_slots(const pe_plan* plan, int n_points, int K, int engine) {
     if (!plan) return -1;
+    if (is_tc(engine)) return pe_tc_slots(plan, n_points);
     int ntiles = (n_points + PE_P - 1) / PE_P;
     int cap = plan->sms * pe_simt_ctas_per_sm(plan, K);
     int s = ntiles < cap ? ntiles : cap;
     return s < 1 ? 1 : s;
 }
 
-extern "C" size_t pe_plan_stash_floats_per_slot(const pe_plan* plan, int K) {
+static size_t simt_stash_floats_per_slot(const pe_plan* plan, int K) { return (size_t)K * PE_P * plan->lay.stash_rows + 64; }
+
+extern "C" size_t pe_plan_scratch_floats(const pe_plan* plan, int n_points, int K, int engine) {
     if (!plan) return 0;
-    return (size_t)K * PE_P * plan->lay.stash_rows + 64;
+    size_t slots = (size_t)pe_plan_slots(plan, n_points, K, engine);
+    if (is_tc(engine)) return slots * pe_tc_stash_floats_per_slot(plan) + pe_tc_image_floats(plan) + 64;
+    return slots * simt_stash_floats_per_slot(plan, K);
 }
 
 extern "C" int pe_pack_params(const pe_plan* plan, const float* h_compact, float* h_padded) {
@@ -180,12 +196,12 @@ extern "C" int pe_residual_loss_grad(const pe_plan* plan, const pe_term_desc* te
     a.stash = d_stash;
     a.n = n_local;
     a.slot_base = slot_base;
-    a.stash_floats = (int)pe_plan_stash_floats_per_slot(plan, K);
+    a.stash_floats = (int)simt_stash_floats_per_slot(plan, K);
     a.inv_n = 1.0f / (float)term->n_global;
-    int slots = pe_plan_slots(plan, n_local, K);
+    int slots = pe_plan_slots(plan, n_local, K, engine);
     if (engine == PE_ENGINE_SIMT_FP32) return pe_launch_resid_simt(plan, a, K, slots, (cudaStream_t)stream);
     if (engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32) {
-        if (!pe_tc_supported(plan, K, engine)) { pe_set_error("tensor-core engine does not support this network/K"); return 1; }
+        if (!pe_engine_supported(plan, term->kind, K, engine)) { pe_set_error("tensor-core engine does not support this residual kind / network (F5, K=5, hidden widths <= 56)"); return 1; }
         return pe_launch_resid_tc(plan, a, K, engine, slots, (cudaStream_t)stream);
     }
     pe_set_error("unknown engine %d", engine);

@@ -1,9 +1,613 @@
-// tcgen05 / TMEM tensor-core engine (placeholder until the UMMA path lands; reports "unsupported").
+// tcgen05 / TMEM tensor-core engine for the collocation residual (F5, K = 5 jet streams, hidden width <= 56).
+//
+// Same math and same C-ABI contract as the SIMT engine (pe_simt.cu); the layer GEMMs of the forward jet pass and of
+// the adjoint pass run on the 5th-generation tensor cores:
+//
+//   forward  layer l : Z_k[128 pts x 64] = A_k[128 x 56] * W_l            (k = value, d/dx, d/dy, d/dt, d2/dt2)
+//   adjoint  layer l : Abar_k[128 x 64] = Zbar_k[128 x 56] * W_l^T
+//
+// fp32 parity on TF32 tensor cores.  kind::tf32 TRUNCATES fp32 operands to 19 bits (measured, profiles/r1_umma_probe.txt),
+// so each product is split A*W ~= A32*Whi + A32*Wlo + Alo*Wbf16 with
+//     A32  = the fp32 activation in shared memory (hardware reads its top 19 bits = Ahi)
+//     Alo  = A - Ahi rounded to bf16, kept in TENSOR MEMORY (A-from-TMEM operand, kind::f16, 2 per column)
+//     Whi/Wlo = tf32 split of the weights, Wbf16 = bf16(W)   (operand images built once per step by tc_prep_kernel)
+// all three accumulate into the same fp32 TMEM accumulator (mixed-kind accumulation, measured exact).  Error per
+// product ~2^-20, i.e. fp32-class (tests hold the engine to the same tolerances as the SIMT engine).
+// PE_ENGINE_TC_TF32 drops the two correction terms (fast mode, ~5e-4).
+//
+// Operand layout (all K-major, no swizzle -- the conventions pinned by tests/probe_umma.py):
+//   activations  ACT[k][chunk c = unit/4][point p][4 fp32]   chunk stride 2064 B (2048 + 16 so that the FFMA
+//                weight-gradient loops below are bank-conflict free), descriptor LBO = 2064, SBO = 128
+//   weights      [chunk = k/4][n][4]  (n = output unit, forward) or (n = input unit, adjoint), LBO = N*16, SBO = 128
+// TMEM (512 columns): accumulators of the 5 streams at columns 64k (k < 5); bf16 Alo operands at 320 + 32k.
+//
+// One CTA (256 threads) per SM, persistent over tiles of 128 points.  Thread (p, h): p = TMEM lane = point,
+// h = warp/4 selects the unit half (chunks 7h..7h+6): all 8 warps run the epilogues (tanh + jet chain rule / its
+// adjoint) straight out of tensor memory with tcgen05.ld and write the next operand back
+// (st.shared 16 B + tcgen05.st), plus the stash the reverse sweep needs (global, L2-resident).
+// The weight-gradient contraction dW_l = sum_{k,p} A_k[p][i] Zbar_k[p][j] (contraction over POINTS) would need
+// MN-major TF32 operands, which tcgen05 only accepts in the SWIZZLE_128B_BASE32B layout (probe); in this round it runs
+// on the FFMA pipe (8x8 register blocks, contraction split over 4 point-quarters inside a warp, shuffle-reduced)
+// concurrently with the asynchronous adjoint MMAs of the same layer.
+#include <cuda_bf16.h>
 #include "pe_common.cuh"
+#include "pe_device.cuh"
 
-int pe_tc_supported(const pe_plan* plan, int K, int engine) { (void)plan; (void)K; (void)engine; return 0; }
-int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st) {
-    (void)plan; (void)a; (void)K; (void)engine; (void)slots; (void)st;
-    pe_set_error("tensor-core engine not built");
+namespace {
+using namespace pe_dev;
+
+constexpr int TC_P = 128;
+constexpr int TC_NCH = 14;                       // 4-float chunks per activation row (K = 56)
+constexpr int TC_CH = 2064;                      // chunk stride in ACT / STAGE (bytes)
+constexpr int TC_ACT_STREAM = TC_NCH * TC_CH;    // 28,896
+constexpr int TC_THREADS = 256;
+constexpr int TC_IMG_HI = 0, TC_IMG_LO = 14336, TC_IMG_BF = 28672, TC_IMG_SET = 36864, TC_IMG_LAYER = 2 * TC_IMG_SET;
+constexpr int TC_STASH_STREAM = TC_NCH * 2048;   // stash is dense: [k][c][p][4]
+constexpr int TC_STASH_LAYER = 5 * TC_STASH_STREAM;
+
+constexpr int SM_ACT = 0;
+constexpr int SM_WIMG = SM_ACT + 5 * TC_ACT_STREAM;          // 144,480
+constexpr int SM_STAGE = SM_WIMG + TC_IMG_SET;               // 181,344
+constexpr int SM_MISC = SM_STAGE + TC_ACT_STREAM;            // 210,240
+constexpr int SM_COORD = SM_MISC + 64;                       // 128 x 4 floats
+constexpr int SM_RED = SM_COORD + 128 * 16;                  // 4 x 64 x 4 floats scratch (layer-1 gradient) / term sums
+constexpr int SM_TOTAL = SM_RED + 4096;
+
+constexpr uint32_t TM_ACC = 0, TM_LO = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t sdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }
+__device__ __forceinline__ uint32_t idesc_bf16(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t id, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t addr, float (&v)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tm_ld8(uint32_t addr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_st2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// bf16 pair of the truncation residues (x - tf32_trunc(x)) of two values, element 0 in the low half
+__device__ __forceinline__ uint32_t lo_pair(float x0, float x1) {
+    float l0 = x0 - __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+    float l1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+    __nv_bfloat162 b = __floats2bfloat162_rn(l0, l1);
+    return *reinterpret_cast<uint32_t*>(&b);
+}
+
+// ---------------------------------------------------------------------------------------------- weight images
+// One block per weight matrix.  Builds, from the padded fp32 parameters, the six tensor-core operand images of the
+// matrix: forward B operand [n = out unit j][k = in unit i] and adjoint B operand [n = i][k = j], each as tf32-hi,
+// tf32-lo (4-float chunks) and bf16 (8-element chunks).  Zero padded to K = 56 (64 for bf16), N = 64.
+__global__ void tc_prep_kernel(const float* __restrict__ params, PeLayout lay, uint8_t* __restrict__ images) {
+    const int m = blockIdx.x;                       // matrix index 0..L-1
+    const int din = lay.d[m], dout = lay.d[m + 1], ldw = lay.ldw[m];
+    const float* W = params + lay.woff[m];
+    uint8_t* img = images + (size_t)m * TC_IMG_LAYER;
+    float* fhi = reinterpret_cast<float*>(img + TC_IMG_HI);
+    float* flo = reinterpret_cast<float*>(img + TC_IMG_LO);
+    __nv_bfloat16* fbf = reinterpret_cast<__nv_bfloat16*>(img + TC_IMG_BF);
+    float* ahi = reinterpret_cast<float*>(img + TC_IMG_SET + TC_IMG_HI);
+    float* alo = reinterpret_cast<float*>(img + TC_IMG_SET + TC_IMG_LO);
+    __nv_bfloat16* abf = reinterpret_cast<__nv_bfloat16*>(img + TC_IMG_SET + TC_IMG_BF);
+    const int NF = (dout <= 16) ? 16 : 64;          // forward N
+    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+        const int i = e >> 6, j = e & 63;
+        const float w = (i < din && j < dout) ? W[(size_t)i * ldw + j] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+        const float lo = w - hi;
+        const __nv_bfloat16 bf = __float2bfloat16_rn(w);
+        if (j < NF) {                               // forward image: rows n = j, K index i
+            if (i < 56) { const int o = (i >> 2) * (NF * 4) + j * 4 + (i & 3); fhi[o] = hi; flo[o] = lo; }
+            fbf[(i >> 3) * (NF * 8) + j * 8 + (i & 7)] = bf;
+        }
+        // adjoint image: rows n = i, K index j
+        if (j < 56) { const int o = (j >> 2) * 256 + i * 4 + (j & 3); ahi[o] = hi; alo[o] = lo; }
+        abf[(j >> 3) * 512 + i * 8 + (j & 7)] = bf;
+    }
+}
+
+struct TcArgs {
+    PeResidArgs r;
+    const uint8_t* images;
+    int fast;            // 1 = single-pass TF32
+};
+
+// ---- issue the MMAs of one layer GEMM for all 5 streams (one thread).  ksteps = K/8 (tf32), kb = K/16 (bf16)
+__device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint32_t wimg_s, int N, int ksteps, int kb, int fast) {
+    const uint32_t id32 = idesc_tf32(N), id16 = idesc_bf16(N);
+    const uint32_t nrow = (uint32_t)N * 16u;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+        const uint32_t d = tbase + TM_ACC + 64u * k;
+        const uint32_t a0 = act_s + (uint32_t)k * TC_ACT_STREAM;
+        for (int s = 0; s < ksteps; ++s)
+            mma_tf32_ss(d, sdesc(a0 + (uint32_t)s * 2u * TC_CH, TC_CH, 128), sdesc(wimg_s + TC_IMG_HI + (uint32_t)s * 2u * nrow, nrow, 128), id32, s > 0);
+        if (!fast) {
+            for (int s = 0; s < ksteps; ++s)
+                mma_tf32_ss(d, sdesc(a0 + (uint32_t)s * 2u * TC_CH, TC_CH, 128), sdesc(wimg_s + TC_IMG_LO + (uint32_t)s * 2u * nrow, nrow, 128), id32, 1);
+            for (int s = 0; s < kb; ++s)
+                mma_bf16_ts(d, tbase + TM_LO + 32u * k + 8u * s, sdesc(wimg_s + TC_IMG_BF + (uint32_t)s * 2u * nrow, nrow, 128), id16, 1);
+        }
+    }
+}
+
+// ---- FFMA weight gradient of one layer: gW[i][j] += sum_{k,p} A_k[p][i] * Z_k[p][j]
+// A_k streams come from the stash through the STAGE buffer (register double buffering), Z_k from ACT.
+// warp w < 7 owns the 8 input units [8w, 8w+8); lane = (q = lane/8: point quarter, jb = lane%8: 8 output units).
+template <bool SMALL_N>
+__device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, const uint8_t* act, uint8_t* stage,
+                                         float* __restrict__ gW, float* __restrict__ gB, int din, int dout, int ldw, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ib = warp;
+    // SMALL_N (dout <= 8): lanes = 32 slices of 4 points, jb = 0;  else lanes = 4 quarters x 8 column blocks (7 used)
+    const int q = SMALL_N ? lane : (lane >> 3);
+    const int jb = SMALL_N ? 0 : (lane & 7);
+    const int npts = SMALL_N ? 4 : 32;
+    const bool active = (ib < 7) && (jb < 7) && (8 * ib < din) && (8 * jb < dout);
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+    float bsum[2] = {0.f, 0.f};
+    float4 pre[7];
+    const float4* src = reinterpret_cast<const float4*>(stash_l);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pre[i] = __ldcg(src + tid + i * TC_THREADS);          // stream 0: 1792 float4
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int e = tid + i * TC_THREADS;                                       // = c*128 + p
+            *reinterpret_cast<float4*>(stage + (e >> 7) * TC_CH + (e & 127) * 16) = pre[i];
+        }
+        __syncthreads();
+        if (k < 4) {
+            const float4* s2 = reinterpret_cast<const float4*>(stash_l + (size_t)(k + 1) * (TC_STASH_STREAM / 4));
+#pragma unroll
+            for (int i = 0; i < 7; ++i) pre[i] = __ldcg(s2 + tid + i * TC_THREADS);
+        }
+        const uint8_t* zk = act + k * TC_ACT_STREAM;
+        if (active) {
+            const uint8_t* pa = stage + (2 * ib) * TC_CH;
+            const uint8_t* pz = zk + (2 * jb) * TC_CH;
+            const int p0 = q * npts;
+#pragma unroll 2
+            for (int s = 0; s < npts; ++s) {
+                const int p = p0 + (SMALL_N ? s : ((s + q) & 31));                    // per-quarter rotation: conflict-free with the 2064 B chunk stride
+                const float4 a0 = *reinterpret_cast<const float4*>(pa + p * 16);
+                const float4 a1 = *reinterpret_cast<const float4*>(pa + TC_CH + p * 16);
+                const float4 z0 = *reinterpret_cast<const float4*>(pz + p * 16);
+                const float4 z1 = *reinterpret_cast<const float4*>(pz + TC_CH + p * 16);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], zv[c], acc[r][c]);
+            }
+        }
+        if (k == 0 && warp == 7) {                                                    // bias gradient: value stream, lanes = units
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int j = lane + 32 * hh;
+                if (j < dout) {
+                    const uint8_t* pz = zk + (j >> 2) * TC_CH + (j & 3) * 4;
+                    float s = 0.f;
+#pragma unroll 8
+                    for (int p = 0; p < TC_P; ++p) s += *reinterpret_cast<const float*>(pz + p * 16);
+                    bsum[hh] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // reduce over the point split inside the warp, then add into the CTA-private gradient partial (fixed owner)
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float v = acc[r][c];
+            if (SMALL_N) {
+                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+            }
+            v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[r][c] = v;
+        }
+    if (active && (SMALL_N ? lane == 0 : lane < 8)) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = 8 * ib + r;
+            if (i < din) {
+                float* dst = gW + (size_t)i * ldw + 8 * jb;
+                if (8 * jb < ldw) {
+                    float4 v = __ldcg(reinterpret_cast<float4*>(dst));
+                    v.x += acc[r][0]; v.y += acc[r][1]; v.z += acc[r][2]; v.w += acc[r][3];
+                    __stcg(reinterpret_cast<float4*>(dst), v);
+                }
+                if (8 * jb + 4 < ldw) {
+                    float4 v = __ldcg(reinterpret_cast<float4*>(dst + 4));
+                    v.x += acc[r][4]; v.y += acc[r][5]; v.z += acc[r][6]; v.w += acc[r][7];
+                    __stcg(reinterpret_cast<float4*>(dst + 4), v);
+                }
+            }
+        }
+    }
+    if (warp == 7) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = lane + 32 * hh;
+            if (j < dout) __stcg(gB + j, __ldcg(gB + j) + bsum[hh]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const PeResidArgs& A = args.r;
+    const PeLayout& lay = A.lay;
+    const pe_term_desc& T = A.term;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = 32 * (warp & 3) + lane;            // TMEM lane = point of the tile
+    const int h = warp >> 2;                         // unit half: chunks [7h, 7h+7)
+    const int L = lay.L;
+    const int fast = args.fast;
+    uint8_t* act = smem + SM_ACT;
+    uint8_t* wimg = smem + SM_WIMG;
+    uint8_t* stage = smem + SM_STAGE;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SM_MISC);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC + 16);
+    float* coord = reinterpret_cast<float*>(smem + SM_COORD);       // [128][4]: a0x, a0y, a0t, valid
+    float* red = reinterpret_cast<float*>(smem + SM_RED);
+    const uint32_t act_s = smem_u32(act), wimg_s = smem_u32(wimg), bar_s = smem_u32(mbar);
+
+    for (int i = tid; i < SM_TOTAL / 16; i += TC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int slot = A.slot_base + blockIdx.x;
+    float* gpart = A.grad_partials + (size_t)slot * lay.total;
+    float* stash = A.stash + (size_t)blockIdx.x * A.stash_floats;
+    const float* __restrict__ params = A.params;
+    for (int i = tid; i < lay.total; i += TC_THREADS) __stcg(gpart + i, 0.f);
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t tlane = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    // zero the bf16 "lo" operand columns once (units 56..63 are never written afterwards and must stay zero)
+    for (int c = h * 80; c < h * 80 + 80; c += 2) tm_st2(tlane + TM_LO + c, 0u, 0u);
+    tm_wait_st();
+    uint32_t parity = 0;
+    float tsum[PE_MAX_TERMS];
+#pragma unroll
+    for (int i = 0; i < PE_MAX_TERMS; ++i) tsum[i] = 0.f;
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    const int ntiles = (A.n + TC_P - 1) / TC_P;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int pt = tile * TC_P + p;
+        const bool valid = pt < A.n;
+        const float* row = A.points + (size_t)(valid ? pt : 0) * T.ld;
+        if (h == 0) {
+            float x = 0.f, y = 0.f, t = 0.f;
+            if (valid) { x = row[0]; y = row[1]; t = row[2]; }
+            *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(fmaf(x, T.in_scale[0], T.in_shift[0]), fmaf(y, T.in_scale[1], T.in_shift[1]),
+                                                                    fmaf(t, T.in_scale[2], T.in_shift[2]), valid ? 1.f : 0.f);
+        }
+        __syncthreads();
+        // ================================================================ layer 1 (3 -> d1): per-thread FFMA
+        {
+            const float4 c4 = *reinterpret_cast<const float4*>(coord + 4 * p);
+            const float* W0 = params + lay.woff[0];
+            const float* b0 = params + lay.boff[0];
+            const int ldw = lay.ldw[0], dout = lay.d[1];
+            float* st = stash;                                         // stash layer index 0 = outputs of layer 1
+#pragma unroll 1
+            for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                float o[5][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = 4 * c + u;
+                    float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (j < dout) {
+                        const float w0 = __ldg(W0 + j), w1 = __ldg(W0 + ldw + j), w2 = __ldg(W0 + 2 * ldw + j);
+                        z[0] = fmaf(c4.x, w0, fmaf(c4.y, w1, c4.z * w2));
+                        z[1] = T.in_scale[0] * w0; z[2] = T.in_scale[1] * w1; z[3] = T.in_scale[2] * w2; z[4] = 0.f;
+                        act_fwd<5>(z, __ldg(b0 + j));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) o[k][u] = z[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float4 v = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+                    *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + c * TC_CH + p * 16) = v;
+                    __stcg(reinterpret_cast<float4*>(st + (size_t)k * (TC_STASH_STREAM / 4) + c * 512 + p * 4), v);
+                    tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(o[k][0], o[k][1]), lo_pair(o[k][2], o[k][3]));
+                }
+            }
+        }
+        // ================================================================ forward: hidden layers 2..L-1 and the output layer L
+        for (int l = 2; l <= L; ++l) {
+            const int m = l - 1;                                       // weight matrix index
+            const int dout = lay.d[l];
+            const int NF = (dout <= 16) ? 16 : 64;
+            {   // forward operand images of matrix m -> smem
+                const float4* src = reinterpret_cast<const float4*>(args.images + (size_t)m * TC_IMG_LAYER);
+                float4* dst = reinterpret_cast<float4*>(wimg);
+                for (int i = tid; i < TC_IMG_SET / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+            }
+            tm_wait_st();
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after();
+                issue_layer(tbase, act_s, wimg_s, NF, (lay.d[l - 1] + 7) >> 3, (lay.d[l - 1] + 15) >> 4, fast);
+                mma_commit(bar_s);
+            }
+            mbar_wait(bar_s, parity);
+            parity ^= 1;
+            fence_after();
+            if (l < L) {
+                const float* bias = params + lay.boff[m];
+                float* st = stash + (size_t)(l - 1) * (TC_STASH_LAYER / 4);
+#pragma unroll 1
+                for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                    float z[5][4];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) tm_ld4(tlane + TM_ACC + 64 * k + 4 * c, z[k]);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = 4 * c + u;
+                        float zz[5];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) zz[k] = z[k][u];
+                        if (j < dout) act_fwd<5>(zz, __ldg(bias + j));
+                        else {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) zz[k] = 0.f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) z[k][u] = zz[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float4 v = make_float4(z[k][0], z[k][1], z[k][2], z[k][3]);
+                        *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + c * TC_CH + p * 16) = v;
+                        __stcg(reinterpret_cast<float4*>(st + (size_t)k * (TC_STASH_STREAM / 4) + c * 512 + p * 4), v);
+                        tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(z[k][0], z[k][1]), lo_pair(z[k][2], z[k][3]));
+                    }
+                }
+            } else if (h == 0) {
+                // ---------------- outputs -> residuals -> loss partials -> seeds (adjoint of the outputs)
+                float Y[5][PE_UJ];
+                const float* bias = params + lay.boff[m];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    float v[8];
+                    tm_ld8(tlane + TM_ACC + 64 * k, v);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < PE_UJ; ++u) Y[k][u] = (u < 8 && u < dout) ? v[u < 8 ? u : 0] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += __ldg(bias + u);
+                const float* aux_row = A.aux ? A.aux + (size_t)(valid ? pt : 0) * 50 : nullptr;
+                residual_stage<5>(Y, T, aux_row, row, valid, A.inv_n, tsum);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float4 v0 = make_float4(Y[k][0], Y[k][1], Y[k][2], Y[k][3]);
+                    const float4 v1 = make_float4(Y[k][4], 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + 0 * TC_CH + p * 16) = v0;
+                    *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + 1 * TC_CH + p * 16) = v1;
+                    tm_st2(tlane + TM_LO + 32 * k + 0, lo_pair(v0.x, v0.y), lo_pair(v0.z, v0.w));
+                    tm_st2(tlane + TM_LO + 32 * k + 2, lo_pair(v1.x, 0.f), 0u);
+                }
+            }
+        }
+        // ================================================================ reverse sweep, layers L .. 2 on tensor cores
+        for (int l = L; l >= 2; --l) {
+            const int m = l - 1;
+            const int din = lay.d[l - 1], dout = lay.d[l];
+            {   // adjoint operand images of matrix m -> smem
+                const float4* src = reinterpret_cast<const float4*>(args.images + (size_t)m * TC_IMG_LAYER + TC_IMG_SET);
+                float4* dst = reinterpret_cast<float4*>(wimg);
+                for (int i = tid; i < TC_IMG_SET / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+            }
+            tm_wait_st();
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after();
+                issue_layer(tbase, act_s, wimg_s, 64, (dout + 7) >> 3, (dout + 15) >> 4, fast);
+                mma_commit(bar_s);
+            }
+            // ---- weight / bias gradient of layer l on the FFMA pipe while the adjoint MMAs run
+            const float* stash_in = stash + (size_t)(l - 2) * (TC_STASH_LAYER / 4);      // outputs of layer l-1
+            if (dout <= 8) dw_layer<true>(stash_in, act, stage, gpart + lay.woff[m], gpart + lay.boff[m], din, dout, lay.ldw[m], tid);
+            else dw_layer<false>(stash_in, act, stage, gpart + lay.woff[m], gpart + lay.boff[m], din, dout, lay.ldw[m], tid);
+            mbar_wait(bar_s, parity);
+            parity ^= 1;
+            fence_after();
+            // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
+#pragma unroll 1
+            for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                float ab[5][4];
+                float4 Av[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) Av[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + c * 512 + p * 4));
+#pragma unroll
+                for (int k = 0; k < 5; ++k) tm_ld4(tlane + TM_ACC + 64 * k + 4 * c, ab[k]);
+                tm_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = 4 * c + u;
+                    float b[5], Aa[5];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        b[k] = ab[k][u];
+                        Aa[k] = (u == 0) ? Av[k].x : (u == 1) ? Av[k].y : (u == 2) ? Av[k].z : Av[k].w;
+                    }
+                    if (j < din) act_bwd<5>(b, Aa);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) b[k] = 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) ab[k][u] = b[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float4 v = make_float4(ab[k][0], ab[k][1], ab[k][2], ab[k][3]);
+                    *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + c * TC_CH + p * 16) = v;
+                    tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(v.x, v.y), lo_pair(v.z, v.w));
+                }
+            }
+        }
+        // ================================================================ layer 1 gradient (3 x d1 + bias): FFMA, fixed-order reduce
+        __syncthreads();
+        {
+            const int d1 = lay.d[1];
+            const int j = tid & 63, qq = tid >> 6;                    // 4 point quarters x 64 units
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, gb = 0.f;
+            if (j < d1) {
+                const uint8_t* base = act + (j >> 2) * TC_CH + (j & 3) * 4;
+#pragma unroll 4
+                for (int s = 0; s < 32; ++s) {
+                    const int pp = 32 * qq + s;
+                    const float4 c4 = *reinterpret_cast<const float4*>(coord + 4 * pp);
+                    const float zv = *reinterpret_cast<const float*>(base + pp * 16);
+                    const float zx = *reinterpret_cast<const float*>(base + 1 * TC_ACT_STREAM + pp * 16);
+                    const float zy = *reinterpret_cast<const float*>(base + 2 * TC_ACT_STREAM + pp * 16);
+                    const float zt = *reinterpret_cast<const float*>(base + 3 * TC_ACT_STREAM + pp * 16);
+                    g0 = fmaf(c4.x, zv, fmaf(T.in_scale[0], zx, g0));
+                    g1 = fmaf(c4.y, zv, fmaf(T.in_scale[1], zy, g1));
+                    g2 = fmaf(c4.z, zv, fmaf(T.in_scale[2], zt, g2));
+                    gb += zv;
+                }
+            }
+            *reinterpret_cast<float4*>(red + (qq * 64 + j) * 4) = make_float4(g0, g1, g2, gb);
+            __syncthreads();
+            if (tid < 64 && tid < d1) {
+                float4 s = *reinterpret_cast<float4*>(red + tid * 4);
+#pragma unroll
+                for (int r = 1; r < 4; ++r) {
+                    const float4 v = *reinterpret_cast<float4*>(red + (r * 64 + tid) * 4);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+                float* gW = gpart + lay.woff[0];
+                const int ldw = lay.ldw[0];
+                __stcg(gW + tid, __ldcg(gW + tid) + s.x);
+                __stcg(gW + ldw + tid, __ldcg(gW + ldw + tid) + s.y);
+                __stcg(gW + 2 * ldw + tid, __ldcg(gW + 2 * ldw + tid) + s.z);
+                float* gB = gpart + lay.boff[0];
+                __stcg(gB + tid, __ldcg(gB + tid) + s.w);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem
+    {
+        float tot[2];
+        tot[0] = warp_sum(tsum[0]);
+        tot[1] = warp_sum(tsum[1]);
+        __syncthreads();
+        if (h == 0 && lane == 0) { red[2 * warp] = tot[0]; red[2 * warp + 1] = tot[1]; }
+        __syncthreads();
+        if (tid == 0) {
+            float* tp = A.term_partials + (size_t)slot * PE_MAX_TERMS;
+#pragma unroll
+            for (int i = 0; i < PE_MAX_TERMS; ++i) tp[i] = 0.f;
+            float s0 = red[0] + red[2] + red[4] + red[6], s1 = red[1] + red[3] + red[5] + red[7];
+            tp[T.term[0]] += s0 * A.inv_n;
+            tp[T.term[1]] += s1 * A.inv_n;
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
+}  // namespace
+
+int pe_tc_supported(const pe_plan* plan, int K, int engine) {
+    (void)engine;
+    const PeLayout& lay = plan->lay;
+    if (K != 5 || lay.d[lay.L] != 5 || lay.L < 2) return 0;
+    for (int l = 1; l < lay.L; ++l)
+        if (lay.d[l] > 56) return 0;     // K = 56 operands, 7 x 8-unit row blocks in the FFMA weight gradient
     return 1;
+}
+
+int pe_tc_slots(const pe_plan* plan, int n_points) {
+    int ntiles = (n_points + TC_P - 1) / TC_P;
+    int s = ntiles < plan->sms ? ntiles : plan->sms;
+    return s < 1 ? 1 : s;
+}
+
+size_t pe_tc_stash_floats_per_slot(const pe_plan* plan) { return (size_t)(plan->lay.L - 1) * (TC_STASH_LAYER / 4) + 64; }
+size_t pe_tc_image_floats(const pe_plan* plan) { return (size_t)plan->lay.L * (TC_IMG_LAYER / 4); }
+
+int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st) {
+    (void)K;
+    TcArgs t;
+    t.r = a;
+    t.fast = (engine == PE_ENGINE_TC_TF32) ? 1 : 0;
+    // scratch layout: [slots x stash floats][weight images]
+    t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
+    uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
+    t.images = images;
+    tc_prep_kernel<<<plan->lay.L, 256, 0, st>>>(a.params, a.lay, images);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { pe_set_error("tc_prep_kernel: %s", cudaGetErrorString(e)); return 3; }
+    e = cudaFuncSetAttribute(resid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024);
+    if (e != cudaSuccess) { pe_set_error("cudaFuncSetAttribute(resid_tc, %d): %s", SM_TOTAL + 1024, cudaGetErrorString(e)); return 2; }
+    resid_tc_kernel<<<slots, TC_THREADS, SM_TOTAL + 1024, st>>>(t);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { pe_set_error("launch resid_tc: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
 }

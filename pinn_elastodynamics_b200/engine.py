@@ -202,10 +202,12 @@ class LossEngine:
         base, stash = 0, 1
         for t in self.terms:
             n = t.hi - t.lo
-            t.slots = self.lib.pe_plan_slots(self.net.plan, max(n, 1), t.K)
+            # the requested engine where it implements the term, the fp32 SIMT engine elsewhere (data / boundary terms)
+            t.engine = self.engine if self.lib.pe_engine_supported(self.net.plan, t.kind, t.K, self.engine) else L.ENGINE_SIMT_FP32
+            t.slots = self.lib.pe_plan_slots(self.net.plan, max(n, 1), t.K, t.engine)
             t.slot_base = base
             base += t.slots
-            stash = max(stash, t.slots * self.lib.pe_plan_stash_floats_per_slot(self.net.plan, t.K))
+            stash = max(stash, self.lib.pe_plan_scratch_floats(self.net.plan, max(n, 1), t.K, t.engine))
         self.n_slots = base
         need = base * self.net.Pp
         if not hasattr(self, 'gpart') or self.gpart.numel() < need:
@@ -233,7 +235,7 @@ class LossEngine:
             if self.kernel_events is not None:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            L.check(self.lib.pe_residual_loss_grad(self.net.plan, C.byref(t.desc), t.K, self.engine,
+            L.check(self.lib.pe_residual_loss_grad(self.net.plan, C.byref(t.desc), t.K, t.engine,
                                                    _ptr(pts), n, _ptr(aux), _ptr(self.net.params),
                                                    _ptr(self.gpart), _ptr(self.tpart), _ptr(self.stash), slots, st),
                     f'pe_residual_loss_grad[{t.name}]')
@@ -241,7 +243,7 @@ class LossEngine:
                 e1.record()
                 self.kernel_events.setdefault(t.name, []).append((e0, e1))
             slots += t.slots
-            self.launches += 1
+            self.launches += 1 if t.engine == L.ENGINE_SIMT_FP32 else 2      # tensor-core engine: operand-image prep + residual kernel
         return slots
 
     def evaluate(self, hist_row=None):

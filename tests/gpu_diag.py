@@ -25,7 +25,7 @@ for K in (1, 2, 4, 5):
 orc = R.Oracle('plate', Ws, bs)
 sets = {'Collo': g['f5_collo'], 'HOLE': g['f5_hole']}
 T, loss, gref = orc.loss_and_grad(sets)
-m = pe.PINN(sets['Collo'], sets['HOLE'], None, None, None, None, None, None, layers, None, None, None, None, verbose=False)
+m = pe.PINN(sets['Collo'], sets['HOLE'], None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine=(sys.argv[1] if len(sys.argv) > 1 else 'simt'))
 m.uv_net.set_weights(Ws, bs)
 m.engine.evaluate(); torch.cuda.synchronize()
 t = m.engine.terms_host(); gc = m.engine.grad_compact_host()
@@ -45,7 +45,9 @@ for tm in m.engine.terms: tm.enabled = True
 rng = np.random.default_rng(0)
 N = 50000
 Collo = rng.uniform([0, 0, 0], [.5, .5, 10], (N, 3)); HOLE = rng.uniform([0, 0, 0], [.1, .1, 10], (N // 10, 3))
-m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False)
+import sys as _s
+ENG = _s.argv[1] if len(_s.argv) > 1 else 'simt'
+m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine=ENG)
 m.uv_net.set_weights(Ws, bs)
 for _ in range(3): m.engine.adam_step(5e-4)
 torch.cuda.synchronize()
@@ -54,4 +56,4 @@ e0.record()
 for _ in range(20): m.engine.adam_step(5e-4)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-print('50k pts: %.3f ms/step  -> %.1f Mpts/s, %.2f TFLOP/s algorithmic' % (ms, N / ms / 1e3, N * 312000 / ms / 1e9))
+print(ENG, '50k pts: %.3f ms/step  -> %.1f Mpts/s, %.2f TFLOP/s algorithmic' % (ms, N / ms / 1e3, N * 312000 / ms / 1e9))

@@ -49,7 +49,7 @@ def _check(m, T_ref, names, g_ref, layers, tol_t, tol_g):
     return t, g
 
 
-@pytest.mark.parametrize('engine', ['simt'])
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
 def test_f5_plain_5x50_random_init(pe, golden, engine):
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
@@ -62,12 +62,13 @@ def test_f5_plain_5x50_random_init(pe, golden, engine):
     _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 1e-5, 2e-5)
 
 
-def test_f5_golden_terms_and_grad(pe, golden):
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_f5_golden_terms_and_grad(pe, golden, engine):
     """zero-bias Xavier init exactly as stored in the golden file"""
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
     Ws, bs = R.xavier_params(layers, seed=1111)
-    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs)
+    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine)
     m.engine.evaluate()
     t = m.engine.terms_host()
     np.testing.assert_allclose(t[:3], g['f5_terms'][:3], rtol=1e-5)
@@ -186,24 +187,26 @@ def test_ragged_and_large_point_counts(pe, n):
     _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 2e-5, 5e-5)
 
 
-def test_bitwise_deterministic(pe, golden):
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_bitwise_deterministic(pe, golden, engine):
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
     Ws, bs = R.xavier_params(layers, seed=1111)
     outs = []
     for _ in range(2):
-        m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs)
+        m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine)
         m.engine.evaluate()
         outs.append(m.engine.out.cpu().numpy().copy())
     assert np.array_equal(outs[0], outs[1])
 
 
-def test_adam_curve_matches_golden(pe, golden):
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_adam_curve_matches_golden(pe, golden, engine):
     """20 Adam steps, post-update losses (plate:496-506) vs the float64 oracle curve."""
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
     Ws, bs = R.xavier_params(layers, seed=1111)
-    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs)
+    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine)
     l_uv, l_s, l_h, loss = m.train(20, 5e-4)
     C = g['f5_curve']
     np.testing.assert_allclose(l_uv, C[:, 0], rtol=1e-5)
@@ -285,3 +288,48 @@ def test_checkpoint_roundtrip_and_layer_assert(pe, tmp_path, golden):
     with pytest.raises(AssertionError):
         pe.PINN(g['f5_collo'][:64], g['f5_hole'][:8], None, None, None, None, None, None, [3, 20, 20, 20, 5], None, None, None, None,
                 uvDir=f, verbose=False)
+
+
+# ------------------------------------------------------------------------------ tensor-core engine specifics
+@pytest.mark.parametrize('n', [1, 127, 128, 129, 128 * 150 + 5])
+def test_tc_ragged_and_large_point_counts(pe, n):
+    """tcgen05 engine: tail tiles (n % 128 != 0), fewer points than a tile, more tiles than SMs; narrow nets (K-steps < 7)"""
+    rng = np.random.default_rng(n)
+    layers = [3, 24, 40, 5]
+    Ws, bs = R.xavier_params(layers, seed=9)
+    bs = random_biases(bs, 4)
+    Collo = rng.uniform([0, 0, 0], [.5, .5, 10], (n, 3))
+    HOLE = rng.uniform([0, 0, 0], [.1, .1, 10], (max(1, n // 7), 3))
+    orc = R.Oracle('plate', Ws, bs)
+    T, loss, gref = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
+    m = _plate(pe, Collo, HOLE, layers, Ws, bs, engine='tc3')
+    assert m.engine.terms[0].engine == 1, 'tensor-core engine was not selected for the collocation term'
+    _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 2e-5, 5e-5)
+
+
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_f5_composite_5x50(pe, golden, engine):
+    """hard-BC composite u = P + D*N (plate:382-387) with the shipped dist/part nets around a 5x50 uv net"""
+    g = golden('plate_ckpt.npz')
+    di, pa = unpack_golden(g, 'dist'), unpack_golden(g, 'part')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=77)
+    bs = random_biases(bs, 8)
+    Collo, HOLE = g['collo'][:1000], g['hole'][:100]
+    orc = R.Oracle('plate', Ws, bs, dist=di, part=pa)
+    T, loss, gref = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
+    m = _plate(pe, Collo, HOLE, layers, Ws, bs, dist=di, part=pa, engine=engine)
+    _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 2e-5, 5e-5)
+
+
+def test_tc_fast_mode_is_tf32_accurate(pe, golden):
+    """PE_ENGINE_TC_TF32 (single-pass TF32, no split): ~1e-3 class, stated separately from the fp32-parity engines"""
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine='tc1')
+    m.engine.evaluate()
+    t = m.engine.terms_host()
+    np.testing.assert_allclose(t[:2], g['f5_terms'][:2], rtol=1e-2)
+    errs = per_layer_grad_err(m.engine.grad_compact_host(), g['f5_grad'], layers)
+    assert max(e for _, e in errs) <= 3e-2, errs
