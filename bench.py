@@ -298,7 +298,7 @@ def main():
             'gpu_launches': launches,
             'e2e': e2e,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
-                         'kernel': 'resid_simt_kernel<5> (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
+                         'kernel': ('resid_simt_kernel<5>' if args.engine == 'simt' else 'resid_tc_kernel (tcgen05)') + ' (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
                          'flop_per_point': FLOP_PER_POINT,
                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in pk else 'fallback',
                          'fp32_ffma_peak_tflops': 148 * 128 * 2 * (clocks['sm_mhz'] or 1965.0) * 1e-6},

@@ -176,11 +176,11 @@ __device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, cons
     const int jb = SMALL_N ? 0 : (lane & 7);
     const int npts = SMALL_N ? 4 : 32;
     const bool active = (ib < 7) && (jb < 7) && (8 * ib < din) && (8 * jb < dout);
-    float acc[8][8];
+    float2 acc2[8][4];            // packed pairs: fma.rn.f32x2 (FFMA2) doubles the fp32 rate of the FMA pipe on sm_100
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc2[r][c] = make_float2(0.f, 0.f);
     float bsum[2] = {0.f, 0.f};
     float4 pre[7];
     const float4* src = reinterpret_cast<const float4*>(stash_l);
@@ -204,7 +204,7 @@ __device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, cons
             const uint8_t* pa = stage + (2 * ib) * TC_CH;
             const uint8_t* pz = zk + (2 * jb) * TC_CH;
             const int p0 = q * npts;
-#pragma unroll 2
+#pragma unroll 4
             for (int s = 0; s < npts; ++s) {
                 const int p = p0 + (SMALL_N ? s : ((s + q) & 31));                    // per-quarter rotation: conflict-free with the 2064 B chunk stride
                 const float4 a0 = *reinterpret_cast<const float4*>(pa + p * 16);
@@ -212,11 +212,13 @@ __device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, cons
                 const float4 z0 = *reinterpret_cast<const float4*>(pz + p * 16);
                 const float4 z1 = *reinterpret_cast<const float4*>(pz + TC_CH + p * 16);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                const float2 zp[4] = {make_float2(z0.x, z0.y), make_float2(z0.z, z0.w), make_float2(z1.x, z1.y), make_float2(z1.z, z1.w)};
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
+                for (int r = 0; r < 8; ++r) {
+                    const float2 ar = make_float2(av[r], av[r]);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], zv[c], acc[r][c]);
+                    for (int c = 0; c < 4; ++c) acc2[r][c] = __ffma2_rn(ar, zp[c], acc2[r][c]);
+                }
             }
         }
         if (k == 0 && warp == 7) {                                                    // bias gradient: value stream, lanes = units
@@ -235,11 +237,12 @@ __device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, cons
         __syncthreads();
     }
     // reduce over the point split inside the warp, then add into the CTA-private gradient partial (fixed owner)
+    float acc[8][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            float v = acc[r][c];
+            float v = (c & 1) ? acc2[r][c >> 1].y : acc2[r][c >> 1].x;
             if (SMALL_N) {
                 v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
             }
@@ -252,16 +255,9 @@ __device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, cons
             const int i = 8 * ib + r;
             if (i < din) {
                 float* dst = gW + (size_t)i * ldw + 8 * jb;
-                if (8 * jb < ldw) {
-                    float4 v = __ldcg(reinterpret_cast<float4*>(dst));
-                    v.x += acc[r][0]; v.y += acc[r][1]; v.z += acc[r][2]; v.w += acc[r][3];
-                    __stcg(reinterpret_cast<float4*>(dst), v);
-                }
-                if (8 * jb + 4 < ldw) {
-                    float4 v = __ldcg(reinterpret_cast<float4*>(dst + 4));
-                    v.x += acc[r][4]; v.y += acc[r][5]; v.z += acc[r][6]; v.w += acc[r][7];
-                    __stcg(reinterpret_cast<float4*>(dst + 4), v);
-                }
+                // red.global.add.v4.f32: no return value, nothing to wait for; one owner thread per element and tile => fixed order
+                if (8 * jb < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+                if (8 * jb + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
             }
         }
     }
@@ -269,7 +265,7 @@ __device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, cons
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const int j = lane + 32 * hh;
-            if (j < dout) __stcg(gB + j, __ldcg(gB + j) + bsum[hh]);
+            if (j < dout) atomicAdd(gB + j, bsum[hh]);
         }
     }
 }
@@ -474,12 +470,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             parity ^= 1;
             fence_after();
             // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
+            float4 Anext[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (7 * h) * 512 + p * 4));
 #pragma unroll 1
             for (int c = 7 * h; c < 7 * h + 7; ++c) {
                 float ab[5][4];
                 float4 Av[5];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) Av[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + c * 512 + p * 4));
+                for (int k = 0; k < 5; ++k) Av[k] = Anext[k];
+                if (c + 1 < 7 * h + 7) {       // prefetch the next chunk's stashed activations (L2 latency hidden behind this chunk's math)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (c + 1) * 512 + p * 4));
+                }
 #pragma unroll
                 for (int k = 0; k < 5; ++k) tm_ld4(tlane + TM_ACC + 64 * k + 4 * c, ab[k]);
                 tm_wait_ld();
