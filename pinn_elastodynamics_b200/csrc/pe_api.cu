@@ -60,6 +60,13 @@ static int build_layout(PeLayout& lay, const int* dims, int n_dims) {
         if (lay.lda[l] > lay.max_lda) lay.max_lda = lay.lda[l];
     }
     lay.stash_rows = rows;
+    int wm = 0, wl = 0;
+    for (int l = 0; l < lay.L; ++l) {
+        if (lay.d[l] * lay.ldw[l] > wm) wm = lay.d[l] * lay.ldw[l];
+        if (lay.ldw[l] > wl) wl = lay.ldw[l];
+    }
+    lay.wmat_floats = wm;
+    lay.wstage_floats = wm + wl;
     int mw = lay.maxw > lay.d[lay.L] ? lay.maxw : lay.d[lay.L];
     lay.groups = (mw + PE_UJ - 1) / PE_UJ;
     if (lay.groups > 16) { pe_set_error("hidden width %d too large (max %d)", lay.maxw, 16 * PE_UJ); return 1; }

@@ -22,6 +22,8 @@ struct PeLayout {
     int maxw;                       // max over d[1..L-1] (hidden widths); d[L] <= PE_UJ required
     int groups;                     // warps per CTA = ceil(max(maxw, d[L]) / PE_UJ)
     int max_lda;                    // max lda over all layers
+    int wmat_floats;                // max over layers of d[l]*ldw[l] (one staged weight matrix)
+    int wstage_floats;              // one weight staging buffer: wmat_floats + max ldw (bias), multiple of 4
 };
 
 struct pe_plan {
@@ -69,4 +71,5 @@ void pe_set_error(const char* fmt, ...);
 int pe_launch_resid_simt(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st);
 int pe_launch_fields(const pe_plan* plan, const PeFieldsArgs& a, int K, cudaStream_t st);
 int pe_simt_smem_bytes(const PeLayout& lay, int K);
+bool pe_simt_stage_weights(const pe_plan* plan, int K);
 int pe_simt_ctas_per_sm(const pe_plan* plan, int K);

@@ -47,14 +47,21 @@ __device__ __forceinline__ void write_input_jets(float* buf, int lda0, int p, fl
     }
 }
 
+// weights come either from the shared-memory staging buffer (WS) or straight from global through L1 (__ldg)
+template <bool WS> __device__ __forceinline__ float2 wld2(const float* p) { return WS ? *reinterpret_cast<const float2*>(p) : __ldg(reinterpret_cast<const float2*>(p)); }
+template <bool WS> __device__ __forceinline__ float4 wld4(const float* p) { return WS ? *reinterpret_cast<const float4*>(p) : __ldg(reinterpret_cast<const float4*>(p)); }
+template <bool WS> __device__ __forceinline__ float wld1(const float* p) { return WS ? *p : __ldg(p); }
+
 // ---- forward GEMM of one layer for thread (p, units j0..j0+9): acc[k][u] = sum_i in[k][p][i] * W[i][j0+u]
-template <int K>
+// packed fp32 FMAs (fma.rn.f32x2 / FFMA2, sm_100): the activation is the broadcast operand, unit pairs are packed
+template <int K, bool WS>
 __device__ __forceinline__ void gemm_fwd(float (&acc)[K][PE_UJ], const float* __restrict__ in, int lda_in, int din,
                                          const float* __restrict__ W, int ldw, int j0, int p) {
+    float2 acc2[K][PE_UJ / 2];
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-        for (int u = 0; u < PE_UJ; ++u) acc[k][u] = 0.f;
+        for (int u = 0; u < PE_UJ / 2; ++u) acc2[k][u] = make_float2(0.f, 0.f);
     const float* wcol = W + j0;
     int i = 0;
     for (; i + 4 <= din; i += 4) {
@@ -66,38 +73,39 @@ __device__ __forceinline__ void gemm_fwd(float (&acc)[K][PE_UJ], const float* __
         }
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
-            float w[PE_UJ];
+            float2 w[PE_UJ / 2];
             const float* wr = wcol + (size_t)(i + ii) * ldw;
 #pragma unroll
-            for (int u2 = 0; u2 < PE_UJ / 2; ++u2) {
-                float2 t = __ldg(reinterpret_cast<const float2*>(wr) + u2);
-                w[2 * u2] = t.x; w[2 * u2 + 1] = t.y;
+            for (int u2 = 0; u2 < PE_UJ / 2; ++u2) w[u2] = wld2<WS>(wr + 2 * u2);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float2 ak = make_float2(a[k][ii], a[k][ii]);
+#pragma unroll
+                for (int u2 = 0; u2 < PE_UJ / 2; ++u2) acc2[k][u2] = __ffma2_rn(ak, w[u2], acc2[k][u2]);
             }
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-#pragma unroll
-                for (int u = 0; u < PE_UJ; ++u) acc[k][u] = fmaf(a[k][ii], w[u], acc[k][u]);
         }
     }
     for (; i < din; ++i) {
-        float w[PE_UJ];
+        float2 w[PE_UJ / 2];
         const float* wr = wcol + (size_t)i * ldw;
 #pragma unroll
-        for (int u2 = 0; u2 < PE_UJ / 2; ++u2) {
-            float2 t = __ldg(reinterpret_cast<const float2*>(wr) + u2);
-            w[2 * u2] = t.x; w[2 * u2 + 1] = t.y;
-        }
+        for (int u2 = 0; u2 < PE_UJ / 2; ++u2) w[u2] = wld2<WS>(wr + 2 * u2);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            float av = in[(k * PE_P + p) * lda_in + i];
+            const float av = in[(k * PE_P + p) * lda_in + i];
+            const float2 ak = make_float2(av, av);
 #pragma unroll
-            for (int u = 0; u < PE_UJ; ++u) acc[k][u] = fmaf(av, w[u], acc[k][u]);
+            for (int u2 = 0; u2 < PE_UJ / 2; ++u2) acc2[k][u2] = __ffma2_rn(ak, w[u2], acc2[k][u2]);
         }
     }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int u2 = 0; u2 < PE_UJ / 2; ++u2) { acc[k][2 * u2] = acc2[k][u2].x; acc[k][2 * u2 + 1] = acc2[k][u2].y; }
 }
 
 // ---- adjoint GEMM: ab[k][u] = sum_j zb[k][p][j] * W[i0+u][j]
-template <int K>
+template <int K, bool WS>
 __device__ __forceinline__ void gemm_adj(float (&ab)[K][PE_UJ], const float* __restrict__ zb, int lda_out, int dout,
                                          const float* __restrict__ W, int ldw, int i0, int p) {
 #pragma unroll
@@ -112,7 +120,7 @@ __device__ __forceinline__ void gemm_adj(float (&ab)[K][PE_UJ], const float* __r
         for (int k = 0; k < K; ++k) z[k] = ld4(zb + (k * PE_P + p) * lda_out + j);
 #pragma unroll
         for (int u = 0; u < PE_UJ; ++u) {
-            float4 w = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)u * ldw + j));
+            float4 w = wld4<WS>(wrow + (size_t)u * ldw + j);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float s = ab[k][u];
@@ -127,7 +135,7 @@ __device__ __forceinline__ void gemm_adj(float (&ab)[K][PE_UJ], const float* __r
         for (int k = 0; k < K; ++k) z[k] = zb[(k * PE_P + p) * lda_out + j];
 #pragma unroll
         for (int u = 0; u < PE_UJ; ++u) {
-            float w = __ldg(wrow + (size_t)u * ldw + j);
+            float w = wld1<WS>(wrow + (size_t)u * ldw + j);
 #pragma unroll
             for (int k = 0; k < K; ++k) ab[k][u] = fmaf(z[k], w, ab[k][u]);
         }
@@ -135,7 +143,19 @@ __device__ __forceinline__ void gemm_adj(float (&ab)[K][PE_UJ], const float* __r
 }
 
 // MAXG = max warps per CTA this instantiation is launched with; MINB = CTAs/SM the register budget allows
-template <int K, int MAXG, int MINB>
+// cooperative copy of weight matrix m (+ its bias) into a staging buffer: one batch of coalesced 128-bit loads per
+// thread instead of din dependent L2 round trips inside the GEMM loop
+__device__ __forceinline__ void stage_weights(float* dst, const float* __restrict__ params, const PeLayout& lay, int m, int tid, int nthr) {
+    const float4* src = reinterpret_cast<const float4*>(params + lay.woff[m]);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const int n4 = (lay.d[m] * lay.ldw[m]) >> 2;
+    for (int i = tid; i < n4; i += nthr) d4[i] = __ldg(src + i);
+    const float4* sb = reinterpret_cast<const float4*>(params + lay.boff[m]);
+    float4* db = reinterpret_cast<float4*>(dst + lay.wmat_floats);
+    for (int i = tid; i < (lay.ldw[m] >> 2); i += nthr) db[i] = __ldg(sb + i);
+}
+
+template <int K, int MAXG, int MINB, bool WS>
 __global__ void __launch_bounds__(PE_P * MAXG, MINB)
 resid_simt_kernel(const PeResidArgs args) {
     extern __shared__ __align__(16) float smem[];
@@ -147,7 +167,11 @@ resid_simt_kernel(const PeResidArgs args) {
     const int bufsz = K * PE_P * lay.max_lda + 16;
     float* buf0 = smem;
     float* buf1 = smem + bufsz;
+    float* wst = smem + 2 * bufsz;                 // WS: two weight staging buffers of lay.wstage_floats
     for (int i = tid; i < 2 * bufsz; i += nthr) smem[i] = 0.f;
+    // weight matrix m of the current layer: staged copy (buffer m & 1) or global
+    auto Wm = [&](int m) -> const float* { return WS ? wst + (m & 1) * lay.wstage_floats : args.params + lay.woff[m]; };
+    auto Bm = [&](int m) -> const float* { return WS ? wst + (m & 1) * lay.wstage_floats + lay.wmat_floats : args.params + lay.boff[m]; };
 
     const int slot = args.slot_base + blockIdx.x;
     float* gpart = args.grad_partials + (size_t)slot * lay.total;
@@ -169,16 +193,18 @@ resid_simt_kernel(const PeResidArgs args) {
         float* cur = buf0;
         float* oth = buf1;
         if (g == 0) write_input_jets<K>(cur, lay.lda[0], p, x, y, t, T.in_scale, T.in_shift);
+        if (WS) stage_weights(wst, params, lay, 0, tid, nthr);
         __syncthreads();
 
         // ------------------------------------------------ forward, hidden layers
         for (int l = 1; l < L; ++l) {
             const int din = lay.d[l - 1], dout = lay.d[l];
             const int j0 = g * PE_UJ;
+            if (WS) stage_weights(wst + (l & 1) * lay.wstage_floats, params, lay, l, tid, nthr);   // next layer's matrix, overlaps this GEMM
             if (j0 < dout) {
                 float acc[K][PE_UJ];
-                gemm_fwd<K>(acc, cur, lay.lda[l - 1], din, params + lay.woff[l - 1], lay.ldw[l - 1], j0, p);
-                const float* bias = params + lay.boff[l - 1] + j0;
+                gemm_fwd<K, WS>(acc, cur, lay.lda[l - 1], din, Wm(l - 1), lay.ldw[l - 1], j0, p);
+                const float* bias = Bm(l - 1) + j0;
                 float* st = stash + (size_t)K * PE_P * lay.soff[l];
                 const int ldo = lay.lda[l];
 #pragma unroll
@@ -187,9 +213,9 @@ resid_simt_kernel(const PeResidArgs args) {
                         float z0[K], z1[K];
 #pragma unroll
                         for (int k = 0; k < K; ++k) { z0[k] = acc[k][u]; z1[k] = acc[k][u + 1]; }
-                        act_fwd<K>(z0, __ldg(bias + u));
+                        act_fwd<K>(z0, wld1<WS>(bias + u));
                         const bool two = (j0 + u + 1 < dout);
-                        if (two) act_fwd<K>(z1, __ldg(bias + u + 1));
+                        if (two) act_fwd<K>(z1, wld1<WS>(bias + u + 1));
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             float2 v = make_float2(z0[k], two ? z1[k] : 0.f);
@@ -208,11 +234,11 @@ resid_simt_kernel(const PeResidArgs args) {
             const int ldo = lay.lda[L];
             if (g == 0) {
                 float Y[K][PE_UJ];
-                gemm_fwd<K>(Y, cur, lay.lda[L - 1], din, params + lay.woff[L - 1], lay.ldw[L - 1], 0, p);
-                const float* bias = params + lay.boff[L - 1];
+                gemm_fwd<K, WS>(Y, cur, lay.lda[L - 1], din, Wm(L - 1), lay.ldw[L - 1], 0, p);
+                const float* bias = Bm(L - 1);
 #pragma unroll
                 for (int u = 0; u < PE_UJ; ++u) {
-                    if (u < dout) Y[0][u] += __ldg(bias + u);
+                    if (u < dout) Y[0][u] += wld1<WS>(bias + u);
                     else {
 #pragma unroll
                         for (int k = 0; k < K; ++k) Y[k][u] = 0.f;
@@ -235,6 +261,8 @@ resid_simt_kernel(const PeResidArgs args) {
         for (int l = L; l >= 1; --l) {
             const int din = lay.d[l - 1], dout = lay.d[l];
             const int ldi = lay.lda[l - 1], ldo = lay.lda[l];
+            // matrices L-1 and L-2 are still staged from the forward pass; deeper ones are prefetched one layer ahead
+            if (WS && l <= L - 1 && l >= 3) stage_weights(wst + ((l - 2) & 1) * lay.wstage_floats, params, lay, l - 2, tid, nthr);
             if (l < L) {
                 if (l == 1) {
                     if (g == 0) write_input_jets<K>(bufA, ldi, p, x, y, t, T.in_scale, T.in_shift);
@@ -254,25 +282,32 @@ resid_simt_kernel(const PeResidArgs args) {
                 for (int task = tid; task < nI * nJ; task += nthr) {
                     const int ib = task / nJ, jb = task - ib * nJ;
                     const int i0 = ib * 4, j0 = jb * 8;
-                    float acc[4][8];
+                    float2 acc2[4][4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+                        for (int c = 0; c < 4; ++c) acc2[r][c] = make_float2(0.f, 0.f);
                     const float* pa = bufA + i0;
                     const float* pz = bufZ + j0;
-#pragma unroll 2
+#pragma unroll 4
                     for (int kp = 0; kp < K * PE_P; ++kp) {
                         float4 a = ld4(pa + kp * ldi);
                         float4 z0 = ld4(pz + kp * ldo);
                         float4 z1 = ld4(pz + kp * ldo + 4);
                         const float av[4] = {a.x, a.y, a.z, a.w};
-                        const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                        const float2 zp[4] = {make_float2(z0.x, z0.y), make_float2(z0.z, z0.w), make_float2(z1.x, z1.y), make_float2(z1.z, z1.w)};
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
+                        for (int r = 0; r < 4; ++r) {
+                            const float2 ar = make_float2(av[r], av[r]);
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], zv[c], acc[r][c]);
+                            for (int c = 0; c < 4; ++c) acc2[r][c] = __ffma2_rn(ar, zp[c], acc2[r][c]);
+                        }
                     }
+                    float acc[4][8];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { acc[r][2 * c] = acc2[r][c].x; acc[r][2 * c + 1] = acc2[r][c].y; }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int i = i0 + r;
@@ -305,7 +340,7 @@ resid_simt_kernel(const PeResidArgs args) {
             const int i0 = g * PE_UJ;
             float ab[K][PE_UJ];
             const bool active = i0 < din;
-            if (active) gemm_adj<K>(ab, bufZ, ldo, dout, params + lay.woff[l - 1], lay.ldw[l - 1], i0, p);
+            if (active) gemm_adj<K, WS>(ab, bufZ, ldo, dout, Wm(l - 1), lay.ldw[l - 1], i0, p);
             __syncthreads();
             if (active) {
 #pragma unroll
@@ -378,7 +413,7 @@ fields_simt_kernel(const PeFieldsArgs args) {
             const int j0 = g * PE_UJ;
             if (j0 < dout) {
                 float acc[K][PE_UJ];
-                gemm_fwd<K>(acc, cur, lay.lda[l - 1], din, params + lay.woff[l - 1], lay.ldw[l - 1], j0, p);
+                gemm_fwd<K, false>(acc, cur, lay.lda[l - 1], din, params + lay.woff[l - 1], lay.ldw[l - 1], j0, p);
                 const float* bias = params + lay.boff[l - 1] + j0;
                 const int ldo = lay.lda[l];
 #pragma unroll
@@ -402,7 +437,7 @@ fields_simt_kernel(const PeFieldsArgs args) {
         if (g == 0) {
             const int din = lay.d[L - 1], dout = lay.d[L];
             float Y[K][PE_UJ];
-            gemm_fwd<K>(Y, cur, lay.lda[L - 1], din, params + lay.woff[L - 1], lay.ldw[L - 1], 0, p);
+            gemm_fwd<K, false>(Y, cur, lay.lda[L - 1], din, params + lay.woff[L - 1], lay.ldw[L - 1], 0, p);
             const float* bias = params + lay.boff[L - 1];
 #pragma unroll
             for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += __ldg(bias + u);
@@ -446,12 +481,21 @@ int pe_simt_smem_bytes(const PeLayout& lay, int K) {
     return 2 * (K * PE_P * lay.max_lda + 16) * (int)sizeof(float);
 }
 
-template <int K, int MAXG, int MINB>
+// weights are staged in shared memory (double buffered) whenever that still leaves the same number of CTAs per SM
+bool pe_simt_stage_weights(const pe_plan* plan, int K) {
+    const PeLayout& lay = plan->lay;
+    int base = pe_simt_smem_bytes(lay, K), extra = 2 * lay.wstage_floats * (int)sizeof(float);
+    int limit = plan->smem_optin > 0 ? plan->smem_optin : 227 * 1024;
+    int by_reg = lay.groups <= 5 ? 2 : 1;
+    return (base + extra + 1024) * by_reg <= limit + 1024 * by_reg && base + extra <= limit;
+}
+
+template <int K, int MAXG, int MINB, bool WS>
 static int launch_resid_g(const PeResidArgs& a, int slots, cudaStream_t st) {
-    int smem = pe_simt_smem_bytes(a.lay, K);
-    cudaError_t e = cudaFuncSetAttribute(resid_simt_kernel<K, MAXG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int smem = pe_simt_smem_bytes(a.lay, K) + (WS ? 2 * a.lay.wstage_floats * (int)sizeof(float) : 0);
+    cudaError_t e = cudaFuncSetAttribute(resid_simt_kernel<K, MAXG, MINB, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { pe_set_error("cudaFuncSetAttribute(resid_simt<%d>, smem=%d): %s", K, smem, cudaGetErrorString(e)); return 2; }
-    resid_simt_kernel<K, MAXG, MINB><<<slots, PE_P * a.lay.groups, smem, st>>>(a);
+    resid_simt_kernel<K, MAXG, MINB, WS><<<slots, PE_P * a.lay.groups, smem, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("launch resid_simt<%d>: %s", K, cudaGetErrorString(e)); return 3; }
     return 0;
@@ -459,10 +503,10 @@ static int launch_resid_g(const PeResidArgs& a, int slots, cudaStream_t st) {
 
 template <int K>
 static int launch_resid(const pe_plan* plan, const PeResidArgs& a, int slots, cudaStream_t st) {
-    (void)plan;
-    if (a.lay.groups <= 5) return launch_resid_g<K, 5, 2>(a, slots, st);
-    if (a.lay.groups <= 8) return launch_resid_g<K, 8, 1>(a, slots, st);
-    return launch_resid_g<K, 16, 1>(a, slots, st);
+    const bool ws = pe_simt_stage_weights(plan, K);
+    if (a.lay.groups <= 5) return ws ? launch_resid_g<K, 5, 2, true>(a, slots, st) : launch_resid_g<K, 5, 2, false>(a, slots, st);
+    if (a.lay.groups <= 8) return ws ? launch_resid_g<K, 8, 1, true>(a, slots, st) : launch_resid_g<K, 8, 1, false>(a, slots, st);
+    return ws ? launch_resid_g<K, 16, 1, true>(a, slots, st) : launch_resid_g<K, 16, 1, false>(a, slots, st);
 }
 
 int pe_launch_resid_simt(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st) {
@@ -502,7 +546,7 @@ int pe_launch_fields(const pe_plan* plan, const PeFieldsArgs& a, int K, cudaStre
 }
 
 int pe_simt_ctas_per_sm(const pe_plan* plan, int K) {
-    int smem = pe_simt_smem_bytes(plan->lay, K);
+    int smem = pe_simt_smem_bytes(plan->lay, K) + (pe_simt_stage_weights(plan, K) ? 2 * plan->lay.wstage_floats * (int)sizeof(float) : 0);
     int by_smem = (plan->smem_optin > 0 ? plan->smem_optin + 1024 : 228 * 1024) / (smem + 1024);
     int by_reg = plan->lay.groups <= 5 ? 2 : 1;     // register budgets of the <K, MAXG, MINB> instantiations
     int n = by_smem < by_reg ? by_smem : by_reg;
