@@ -62,7 +62,9 @@ static int build_layout(PeLayout& lay, const int* dims, int n_dims) {
     lay.stash_rows = rows;
     int wm = 0, wl = 0;
     for (int l = 0; l < lay.L; ++l) {
-        if (lay.d[l] * lay.ldw[l] > wm) wm = lay.d[l] * lay.ldw[l];
+        // rows rounded up to whole 10-unit groups: the adjoint GEMM of a partial group reads (and discards) rows past the matrix
+        const int rows = (lay.d[l] + PE_UJ - 1) / PE_UJ * PE_UJ;
+        if (rows * lay.ldw[l] + 16 > wm) wm = rows * lay.ldw[l] + 16;
         if (lay.ldw[l] > wl) wl = lay.ldw[l];
     }
     lay.wmat_floats = wm;

@@ -1,0 +1,62 @@
+"""Multi-GPU sharding invariance (needs >= 2 GPUs): 2 NCCL ranks on the sharded point sets reproduce the 1-rank loss terms,
+gradient and Adam trajectory."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from oracle import ref_torch as R
+import pinn_elastodynamics_b200 as pe
+local = int(os.environ.get('LOCAL_RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+rng = np.random.default_rng(3)
+layers = [3] + 3 * [50] + [5]
+Collo = rng.uniform([0, 0, 0], [.5, .5, 10], (3001, 3)); HOLE = rng.uniform([0, 0, 0], [.1, .1, 10], (333, 3))
+m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine=sys.argv[1])
+Ws, bs = R.xavier_params(layers, seed=8); m.uv_net.set_weights(Ws, bs)
+m.engine.evaluate()
+t0 = m.engine.terms_host().tolist(); g0 = m.engine.grad_compact_host().astype(float)
+curve = m.train(5, 5e-4)[3]
+if int(os.environ.get('RANK', '0')) == 0:
+    print('RESULT ' + json.dumps({'terms': t0, 'gnorm': float(np.linalg.norm(g0)), 'g': g0[::97].tolist(), 'curve': curve, 'params': m.uv_net.get_flat()[::97].astype(float).tolist()}))
+if world > 1:
+    dist.destroy_process_group()
+''' % ROOT
+
+
+def _run(world, engine, tmp_path):
+    f = tmp_path / 'w.py'
+    f.write_text(WORKER)
+    if world == 1:
+        cmd = [sys.executable, str(f), engine]
+    else:
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
+               '--master-port', '29611', str(f), engine]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith('RESULT ')]
+    assert line, r.stdout[-2000:] + r.stderr[-2000:]
+    return json.loads(line[0][7:])
+
+
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_two_gpus_match_one(engine, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    a, b = _run(1, engine, tmp_path), _run(2, engine, tmp_path)
+    np.testing.assert_allclose(b['terms'][:3], a['terms'][:3], rtol=2e-6)
+    np.testing.assert_allclose(b['g'], a['g'], rtol=1e-4, atol=1e-6 * a['gnorm'])
+    np.testing.assert_allclose(b['curve'], a['curve'], rtol=1e-5)
+    np.testing.assert_allclose(b['params'], a['params'], rtol=1e-5, atol=1e-7)
