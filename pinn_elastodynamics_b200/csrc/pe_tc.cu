@@ -163,111 +163,36 @@ __device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint
     }
 }
 
-// ---- FFMA weight gradient of one layer: gW[i][j] += sum_{k,p} A_k[p][i] * Z_k[p][j]
-// A_k streams come from the stash through the STAGE buffer (register double buffering), Z_k from ACT.
-// warp w < 7 owns the 8 input units [8w, 8w+8); lane = (q = lane/8: point quarter, jb = lane%8: 8 output units).
-template <bool SMALL_N>
-__device__ __forceinline__ void dw_layer(const float* __restrict__ stash_l, const uint8_t* act, uint8_t* stage,
-                                         float* __restrict__ gW, float* __restrict__ gB, int din, int dout, int ldw, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int ib = warp;
-    // SMALL_N (dout <= 8): lanes = 32 slices of 4 points, jb = 0;  else lanes = 4 quarters x 8 column blocks (7 used)
-    const int q = SMALL_N ? lane : (lane >> 3);
-    const int jb = SMALL_N ? 0 : (lane & 7);
-    const int npts = SMALL_N ? 4 : 32;
-    const bool active = (ib < 7) && (jb < 7) && (8 * ib < din) && (8 * jb < dout);
-    float2 acc2[8][4];            // packed pairs: fma.rn.f32x2 (FFMA2) doubles the fp32 rate of the FMA pipe on sm_100
+// ---------------------------------------------------------------------------------------------- weight gradient on tensor cores
+// dW[i][j] = sum_{k,p} A_k[p][i] * Zbar_k[p][j] contracts over POINTS: both operands are "MN-major" (unit-contiguous).
+// tcgen05 accepts MN-major 16-bit operands in the no-swizzle layout [chunk of 8 units][point][8] (probe), but MN-major
+// TF32 only in SWIZZLE_128B_BASE32B.  So the two operands are split into bf16 (hi, mid) pairs (16 mantissa bits) and the
+// product is hh + hm + mh on kind::f16 (error ~4e-7 of the block maximum, tests/ + /oracle emulation), accumulated over
+// the 5 streams in one M=64 x N<=56 fp32 TMEM tile that aliases the (dead at that point) bf16 "lo" operand columns.
+// Row 63 of the A operand of the value stream is a row of ones: D[63][j] = sum_p Zbar_0[p][j] = bias gradient, for free.
+constexpr int DW_AHI = SM_WIMG, DW_AMID = SM_WIMG + 16384;        // [8 chunks][128 points][8 bf16]
+constexpr int DW_ZHI = SM_STAGE, DW_ZMID = SM_STAGE + 14336;      // [7 chunks][128 points][8 bf16]
+
+__device__ __forceinline__ uint32_t idesc_bf16_mn(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+// 8 fp32 -> 8 bf16 (hi) and 8 bf16 (mid = bf16(x - hi)), packed as two uint4
+__device__ __forceinline__ void split8(const float4& v0, const float4& v1, uint4& hi, uint4& mid) {
+    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t h[4], m[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc2[r][c] = make_float2(0.f, 0.f);
-    float bsum[2] = {0.f, 0.f};
-    float4 pre[7];
-    const float4* src = reinterpret_cast<const float4*>(stash_l);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) pre[i] = __ldcg(src + tid + i * TC_THREADS);          // stream 0: 1792 float4
-#pragma unroll 1
-    for (int k = 0; k < 5; ++k) {
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int e = tid + i * TC_THREADS;                                       // = c*128 + p
-            *reinterpret_cast<float4*>(stage + (e >> 7) * TC_CH + (e & 127) * 16) = pre[i];
-        }
-        __syncthreads();
-        if (k < 4) {
-            const float4* s2 = reinterpret_cast<const float4*>(stash_l + (size_t)(k + 1) * (TC_STASH_STREAM / 4));
-#pragma unroll
-            for (int i = 0; i < 7; ++i) pre[i] = __ldcg(s2 + tid + i * TC_THREADS);
-        }
-        const uint8_t* zk = act + k * TC_ACT_STREAM;
-        if (active) {
-            const uint8_t* pa = stage + (2 * ib) * TC_CH;
-            const uint8_t* pz = zk + (2 * jb) * TC_CH;
-            const int p0 = q * npts;
-#pragma unroll 4
-            for (int s = 0; s < npts; ++s) {
-                const int p = p0 + (SMALL_N ? s : ((s + q) & 31));                    // per-quarter rotation: conflict-free with the 2064 B chunk stride
-                const float4 a0 = *reinterpret_cast<const float4*>(pa + p * 16);
-                const float4 a1 = *reinterpret_cast<const float4*>(pa + TC_CH + p * 16);
-                const float4 z0 = *reinterpret_cast<const float4*>(pz + p * 16);
-                const float4 z1 = *reinterpret_cast<const float4*>(pz + TC_CH + p * 16);
-                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float2 zp[4] = {make_float2(z0.x, z0.y), make_float2(z0.z, z0.w), make_float2(z1.x, z1.y), make_float2(z1.z, z1.w)};
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const float2 ar = make_float2(av[r], av[r]);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc2[r][c] = __ffma2_rn(ar, zp[c], acc2[r][c]);
-                }
-            }
-        }
-        if (k == 0 && warp == 7) {                                                    // bias gradient: value stream, lanes = units
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int j = lane + 32 * hh;
-                if (j < dout) {
-                    const uint8_t* pz = zk + (j >> 2) * TC_CH + (j & 3) * 4;
-                    float s = 0.f;
-#pragma unroll 8
-                    for (int p = 0; p < TC_P; ++p) s += *reinterpret_cast<const float*>(pz + p * 16);
-                    bsum[hh] = s;
-                }
-            }
-        }
-        __syncthreads();
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(hb);
+        __nv_bfloat162 mb = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<uint32_t*>(&hb);
+        m[i] = *reinterpret_cast<uint32_t*>(&mb);
     }
-    // reduce over the point split inside the warp, then add into the CTA-private gradient partial (fixed owner)
-    float acc[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float v = (c & 1) ? acc2[r][c >> 1].y : acc2[r][c >> 1].x;
-            if (SMALL_N) {
-                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
-            }
-            v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
-            acc[r][c] = v;
-        }
-    if (active && (SMALL_N ? lane == 0 : lane < 8)) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int i = 8 * ib + r;
-            if (i < din) {
-                float* dst = gW + (size_t)i * ldw + 8 * jb;
-                // red.global.add.v4.f32: no return value, nothing to wait for; one owner thread per element and tile => fixed order
-                if (8 * jb < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
-                if (8 * jb + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
-            }
-        }
-    }
-    if (warp == 7) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int j = lane + 32 * hh;
-            if (j < dout) atomicAdd(gB + j, bsum[hh]);
-        }
-    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    mid = make_uint4(m[0], m[1], m[2], m[3]);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs args) {
@@ -462,13 +387,105 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 issue_layer(tbase, act_s, wimg_s, 64, (dout + 7) >> 3, (dout + 15) >> 4, fast);
                 mma_commit(bar_s);
             }
-            // ---- weight / bias gradient of layer l on the FFMA pipe while the adjoint MMAs run
-            const float* stash_in = stash + (size_t)(l - 2) * (TC_STASH_LAYER / 4);      // outputs of layer l-1
-            if (dout <= 8) dw_layer<true>(stash_in, act, stage, gpart + lay.woff[m], gpart + lay.boff[m], din, dout, lay.ldw[m], tid);
-            else dw_layer<false>(stash_in, act, stage, gpart + lay.woff[m], gpart + lay.boff[m], din, dout, lay.ldw[m], tid);
-            mbar_wait(bar_s, parity);
+            // ---- weight / bias gradient of layer l on the tensor cores (bf16 hi/mid operands, see above)
+            const float* stash_in = stash + (size_t)(l - 2) * (TC_STASH_LAYER / 4);      // outputs of layer l-1 = inputs A of layer l
+            const int NZ = (dout + 7) & ~7;                                              // N of the dW tile
+            const int zc8 = NZ >> 3;                                                     // 8-unit chunks of Zbar
+            float4 pre[4][2];
+            auto load_A = [&](int k) {                                                   // stash (L2) -> registers, tasks (c8 < 7, p)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = tid + i * TC_THREADS;
+                    if (t < 7 * TC_P) {
+                        const int c8 = t >> 7, pp = t & 127;
+                        const float* src = stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (2 * c8) * 512 + pp * 4;
+                        pre[i][0] = __ldcg(reinterpret_cast<const float4*>(src));
+                        pre[i][1] = __ldcg(reinterpret_cast<const float4*>(src + 512));
+                    }
+                }
+            };
+            auto store_A = [&](int k) {                                                  // registers -> bf16 hi/mid operand images
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = tid + i * TC_THREADS;
+                    if (t < 7 * TC_P) {
+                        const int c8 = t >> 7, pp = t & 127;
+                        uint4 hi, mid;
+                        split8(pre[i][0], pre[i][1], hi, mid);
+                        *reinterpret_cast<uint4*>(smem + DW_AHI + c8 * 2048 + pp * 16) = hi;
+                        *reinterpret_cast<uint4*>(smem + DW_AMID + c8 * 2048 + pp * 16) = mid;
+                    }
+                }
+                if (tid < TC_P) {                                                        // chunk 7: units 56..63, unit 63 = ones row of the value stream
+                    const uint32_t one_hi = (k == 0) ? 0x3F800000u : 0u;                 // bf16(1.0) in the high half = element 7
+                    *reinterpret_cast<uint4*>(smem + DW_AHI + 7 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, one_hi);
+                    *reinterpret_cast<uint4*>(smem + DW_AMID + 7 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            auto conv_Z = [&](int k) {                                                   // ACT[k] (fp32, smem) -> bf16 hi/mid images
+                for (int t = tid; t < zc8 * TC_P; t += TC_THREADS) {
+                    const int c8 = t >> 7, pp = t & 127;
+                    const uint8_t* src = act + k * TC_ACT_STREAM + (2 * c8) * TC_CH + pp * 16;
+                    uint4 hi, mid;
+                    split8(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + TC_CH), hi, mid);
+                    *reinterpret_cast<uint4*>(smem + DW_ZHI + c8 * 2048 + pp * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + DW_ZMID + c8 * 2048 + pp * 16) = mid;
+                }
+            };
+            load_A(0);
+            conv_Z(0);                                   // STAGE region: free while the adjoint MMAs read WIMG / ACT / LO
+            mbar_wait(bar_s, parity);                    // adjoint MMAs done: WIMG region and the LO columns are free now
             parity ^= 1;
             fence_after();
+#pragma unroll 1
+            for (int k = 0; k < 5; ++k) {
+                store_A(k);
+                if (k > 0) conv_Z(k);
+                fence_async_smem();
+                fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after();
+                    const uint32_t id = idesc_bf16_mn(64, NZ);
+                    const uint32_t d = tbase + TM_LO;
+                    const uint32_t ahi = smem_u32(smem + DW_AHI), amid = smem_u32(smem + DW_AMID);
+                    const uint32_t zhi = smem_u32(smem + DW_ZHI), zmid = smem_u32(smem + DW_ZMID);
+#pragma unroll 1
+                    for (int s8 = 0; s8 < 8; ++s8) {     // 16 points per MMA
+                        const uint32_t o = (uint32_t)s8 * 256u;
+                        mma_bf16_ss(d, sdesc(ahi + o, 128, 2048), sdesc(zhi + o, 128, 2048), id, (k > 0 || s8 > 0) ? 1u : 0u);
+                        mma_bf16_ss(d, sdesc(ahi + o, 128, 2048), sdesc(zmid + o, 128, 2048), id, 1u);
+                        mma_bf16_ss(d, sdesc(amid + o, 128, 2048), sdesc(zhi + o, 128, 2048), id, 1u);
+                    }
+                    mma_commit(bar_s);
+                }
+                if (k < 4) load_A(k + 1);                // in flight while the MMAs of stream k run
+                mbar_wait(bar_s, parity);
+                parity ^= 1;
+            }
+            fence_after();
+            {   // drain the dW tile: rows i = 16*quadrant + lane (lane < 16), row 63 = bias gradient; h selects the column half
+                const int quad = warp & 3;
+                const int i = 16 * quad + lane;
+                const int ldw = lay.ldw[m];
+                float* gW = gpart + lay.woff[m];
+                float* gB = gpart + lay.boff[m];
+                const int c_lo = h ? 32 : 0, c_hi = h ? 56 : 32;
+                for (int c = c_lo; c < c_hi; c += 8) {
+                    float v[8];
+                    tm_ld8(tlane + TM_LO + c, v);
+                    tm_wait_ld();
+                    if (lane < 16 && c < NZ) {
+                        float* dst = (i < din) ? gW + (size_t)i * ldw + c : ((i == 63) ? gB + c : nullptr);
+                        if (dst) {
+                            if (c < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+                            if (c + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+                        }
+                    }
+                }
+                // the tile aliased the lo-operand columns of streams 0/1 including stream 0's zero pad (units 56..63): restore it
+                if (h == 0) { tm_st2(tlane + TM_LO + 28, 0u, 0u); tm_st2(tlane + TM_LO + 30, 0u, 0u); }
+            }
             // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
             float4 Anext[5];
 #pragma unroll

@@ -102,6 +102,26 @@ def t_mnmajor_tf32(M=64, N=64, P=128, swap=False):
     return np.array_equal(got, exp), untouched, got, exp
 
 
+def t_mnmajor_bf16(M=64, N=56, P=128, swap=False, three=False):
+    """weight-gradient shape on 16-bit operands: D[i][j] = sum_p A[p][i] Z[p][j], both stored [chunk of 8 units][point][8 bf16]
+    (unit-contiguous = MN-major), K = points, 16 per MMA.  three=True: bf16x2 split products hh + hm + mh."""
+    rng = np.random.default_rng(6)
+    A = rng.integers(-3, 4, (P, M)).astype(np.float32)
+    Z = rng.integers(-3, 4, (P, N)).astype(np.float32)
+    ia, iz = chunked(bf16_bits(A), 8), chunked(bf16_bits(Z), 8)          # [ic][p][8]
+    smem = np.concatenate([ia.ravel().view(np.uint8), iz.ravel().view(np.uint8)])
+    offz = ia.size * 2
+    sbo, lbo = P * 16, 128
+    if swap:
+        sbo, lbo = lbo, sbo
+    mm = [(1, sdesc(s * 256, lbo, sbo), sdesc(offz + s * 256, lbo, sbo), idesc(1, M, N, 1, 1), 0, 1 if s else 0) for s in range(P // 16)]
+    out = run(smem, mm, 64)
+    exp = A.T @ Z
+    lanes = np.concatenate([np.arange(16) + 32 * q for q in range(4)]) if M == 64 else np.arange(128)
+    got = out[lanes][:, :N]
+    return np.array_equal(got, exp), got, exp
+
+
 def t_bf16_ss(K=16, N=64):
     rng = np.random.default_rng(3)
     A = rng.integers(-3, 4, (128, K)).astype(np.float32)
@@ -159,6 +179,8 @@ TESTS = [('kmajor tf32 K=8', lambda: t_kmajor_tf32()), ('kmajor tf32 K=8 swapped
          ('mnmajor tf32 M=64 N=8', lambda: t_mnmajor_tf32(N=8)),
          ('bf16 SS K=16', lambda: t_bf16_ss()), ('bf16 SS K=64', lambda: t_bf16_ss(K=64)),
          ('bf16 TS K=16', lambda: t_bf16_ts()), ('bf16 TS K=64', lambda: t_bf16_ts(K=64)), ('mixed tf32 SS + bf16 TS accumulate', lambda: t_bf16_ts(K=64, mixed=True)),
+         ('mnmajor bf16 M=64 N=56', lambda: t_mnmajor_bf16()), ('mnmajor bf16 swapped', lambda: t_mnmajor_bf16(swap=True)),
+         ('mnmajor bf16 M=128 N=64', lambda: t_mnmajor_bf16(M=128, N=64)),
          ('tf32 conversion', None)]
 
 
