@@ -142,7 +142,11 @@ struct TcArgs {
     PeResidArgs r;
     const uint8_t* images;
     int fast;            // 1 = single-pass TF32
+    unsigned long long* prof;   // optional: 16 phase-cycle counters written by CTA 0 / thread 0 (pe_debug_set_tc_profile)
 };
+
+// phase timing (debug): CTA 0, thread 0 accumulates clock64 deltas per phase
+#define TC_PROF(slot) do { if (args.prof && blockIdx.x == 0 && tid == 0) { long long now_ = clock64(); prof_acc[slot] += (unsigned long long)(now_ - prof_t); prof_t = now_; } } while (0)
 
 // ---- issue the MMAs of one layer GEMM for all 5 streams (one thread).  ksteps = K/8 (tf32), kb = K/16 (bf16)
 __device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint32_t wimg_s, int N, int ksteps, int kb, int fast) {
@@ -238,6 +242,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     for (int c = h * 80; c < h * 80 + 80; c += 2) tm_st2(tlane + TM_LO + c, 0u, 0u);
     tm_wait_st();
     uint32_t parity = 0;
+    unsigned long long prof_acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) prof_acc[i] = 0ull;
+    long long prof_t = clock64();
     float tsum[PE_MAX_TERMS];
 #pragma unroll
     for (int i = 0; i < PE_MAX_TERMS; ++i) tsum[i] = 0.f;
@@ -257,6 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                                                                     fmaf(t, T.in_scale[2], T.in_shift[2]), valid ? 1.f : 0.f);
         }
         __syncthreads();
+        TC_PROF(15);
         // ================================================================ layer 1 (3 -> d1): per-thread FFMA
         {
             const float4 c4 = *reinterpret_cast<const float4*>(coord + 4 * p);
@@ -289,6 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 }
             }
         }
+        TC_PROF(0);
         // ================================================================ forward: hidden layers 2..L-1 and the output layer L
         for (int l = 2; l <= L; ++l) {
             const int m = l - 1;                                       // weight matrix index
@@ -303,14 +313,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             fence_async_smem();
             fence_before();
             __syncthreads();
+            TC_PROF(1);
             if (tid == 0) {
                 fence_after();
                 issue_layer(tbase, act_s, wimg_s, NF, (lay.d[l - 1] + 7) >> 3, (lay.d[l - 1] + 15) >> 4, fast);
                 mma_commit(bar_s);
             }
+            TC_PROF(2);
             mbar_wait(bar_s, parity);
             parity ^= 1;
             fence_after();
+            TC_PROF(3);
             if (l < L) {
                 const float* bias = params + lay.boff[m];
                 float* st = stash + (size_t)(l - 1) * (TC_STASH_LAYER / 4);
@@ -369,6 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 }
             }
         }
+        TC_PROF(4);
         // ================================================================ reverse sweep, layers L .. 2 on tensor cores
         for (int l = L; l >= 2; --l) {
             const int m = l - 1;
@@ -382,11 +396,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             fence_async_smem();
             fence_before();
             __syncthreads();
+            TC_PROF(6);
             if (tid == 0) {
                 fence_after();
                 issue_layer(tbase, act_s, wimg_s, 64, (dout + 7) >> 3, (dout + 15) >> 4, fast);
                 mma_commit(bar_s);
             }
+            TC_PROF(7);
             // ---- weight / bias gradient of layer l on the tensor cores (bf16 hi/mid operands, see above)
             const float* stash_in = stash + (size_t)(l - 2) * (TC_STASH_LAYER / 4);      // outputs of layer l-1 = inputs A of layer l
             const int NZ = (dout + 7) & ~7;                                              // N of the dW tile
@@ -437,6 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             mbar_wait(bar_s, parity);                    // adjoint MMAs done: WIMG region and the LO columns are free now
             parity ^= 1;
             fence_after();
+            TC_PROF(8);
 #pragma unroll 1
             for (int k = 0; k < 5; ++k) {
                 store_A(k);
@@ -444,6 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 fence_async_smem();
                 fence_before();
                 __syncthreads();
+                TC_PROF(9);
                 if (tid == 0) {
                     fence_after();
                     const uint32_t id = idesc_bf16_mn(64, NZ);
@@ -459,9 +477,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     }
                     mma_commit(bar_s);
                 }
+                TC_PROF(10);
                 if (k < 4) load_A(k + 1);                // in flight while the MMAs of stream k run
                 mbar_wait(bar_s, parity);
                 parity ^= 1;
+                TC_PROF(11);
             }
             fence_after();
             {   // drain the dW tile: rows i = 16*quadrant + lane (lane < 16), row 63 = bias gradient; h selects the column half
@@ -486,6 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 // the tile aliased the lo-operand columns of streams 0/1 including stream 0's zero pad (units 56..63): restore it
                 if (h == 0) { tm_st2(tlane + TM_LO + 28, 0u, 0u); tm_st2(tlane + TM_LO + 30, 0u, 0u); }
             }
+            TC_PROF(12);
             // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
             float4 Anext[5];
 #pragma unroll
@@ -528,6 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 }
             }
         }
+        TC_PROF(13);
         // ================================================================ layer 1 gradient (3 x d1 + bias): FFMA, fixed-order reduce
         __syncthreads();
         {
@@ -570,6 +592,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             __syncthreads();
         }
     }
+    TC_PROF(14);
+    if (args.prof && blockIdx.x == 0 && tid == 0)
+        for (int i = 0; i < 16; ++i) atomicAdd(args.prof + i, prof_acc[i]);
     // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem
     {
         float tot[2];
@@ -612,10 +637,14 @@ int pe_tc_slots(const pe_plan* plan, int n_points) {
 size_t pe_tc_stash_floats_per_slot(const pe_plan* plan) { return (size_t)(plan->lay.L - 1) * (TC_STASH_LAYER / 4) + 64; }
 size_t pe_tc_image_floats(const pe_plan* plan) { return (size_t)plan->lay.L * (TC_IMG_LAYER / 4); }
 
+static unsigned long long* g_tc_prof = nullptr;
+extern "C" void pe_debug_set_tc_profile(unsigned long long* d_counters16) { g_tc_prof = d_counters16; }
+
 int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st) {
     (void)K;
     TcArgs t;
     t.r = a;
+    t.prof = g_tc_prof;
     t.fast = (engine == PE_ENGINE_TC_TF32) ? 1 : 0;
     // scratch layout: [slots x stash floats][weight images]
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
