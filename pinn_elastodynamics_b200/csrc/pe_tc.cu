@@ -148,21 +148,27 @@ struct TcArgs {
 // phase timing (debug): CTA 0, thread 0 accumulates clock64 deltas per phase
 #define TC_PROF(slot) do { if (args.prof && blockIdx.x == 0 && tid == 0) { long long now_ = clock64(); prof_acc[slot] += (unsigned long long)(now_ - prof_t); prof_t = now_; } } while (0)
 
-// ---- issue the MMAs of one layer GEMM for all 5 streams (one thread).  ksteps = K/8 (tf32), kb = K/16 (bf16)
+// ---- issue the MMAs of one layer GEMM for all 5 streams (one thread).  ksteps = K/8 (tf32), kb = K/16 (bf16).
+// Descriptors are built once; a K-step only adds a constant to the 14-bit start-address field (no carry: smem < 256 KB).
 __device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint32_t wimg_s, int N, int ksteps, int kb, int fast) {
     const uint32_t id32 = idesc_tf32(N), id16 = idesc_bf16(N);
     const uint32_t nrow = (uint32_t)N * 16u;
+    const uint64_t a_step = (uint64_t)((2u * TC_CH) >> 4), b_step = (uint64_t)((2u * nrow) >> 4);
+    const uint64_t b_hi = sdesc(wimg_s + TC_IMG_HI, nrow, 128), b_lo = sdesc(wimg_s + TC_IMG_LO, nrow, 128), b_bf = sdesc(wimg_s + TC_IMG_BF, nrow, 128);
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
         const uint32_t d = tbase + TM_ACC + 64u * k;
-        const uint32_t a0 = act_s + (uint32_t)k * TC_ACT_STREAM;
-        for (int s = 0; s < ksteps; ++s)
-            mma_tf32_ss(d, sdesc(a0 + (uint32_t)s * 2u * TC_CH, TC_CH, 128), sdesc(wimg_s + TC_IMG_HI + (uint32_t)s * 2u * nrow, nrow, 128), id32, s > 0);
+        const uint64_t a0 = sdesc(act_s + (uint32_t)k * TC_ACT_STREAM, TC_CH, 128);
+#pragma unroll
+        for (int s = 0; s < 7; ++s)
+            if (s < ksteps) mma_tf32_ss(d, a0 + s * a_step, b_hi + s * b_step, id32, s > 0);
         if (!fast) {
-            for (int s = 0; s < ksteps; ++s)
-                mma_tf32_ss(d, sdesc(a0 + (uint32_t)s * 2u * TC_CH, TC_CH, 128), sdesc(wimg_s + TC_IMG_LO + (uint32_t)s * 2u * nrow, nrow, 128), id32, 1);
-            for (int s = 0; s < kb; ++s)
-                mma_bf16_ts(d, tbase + TM_LO + 32u * k + 8u * s, sdesc(wimg_s + TC_IMG_BF + (uint32_t)s * 2u * nrow, nrow, 128), id16, 1);
+#pragma unroll
+            for (int s = 0; s < 7; ++s)
+                if (s < ksteps) mma_tf32_ss(d, a0 + s * a_step, b_lo + s * b_step, id32, 1);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s < kb) mma_bf16_ts(d, tbase + TM_LO + 32u * k + 8u * s, b_bf + s * b_step, id16, 1);
         }
     }
 }
@@ -253,6 +259,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     __syncthreads();
     fence_after();
 
+    float4 img[9];                                   // one operand-image set (36,864 B / 256 threads), prefetched a phase ahead
+#pragma unroll
+    for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(args.images + (size_t)1 * TC_IMG_LAYER) + tid + i * TC_THREADS);
     const int ntiles = (A.n + TC_P - 1) / TC_P;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int pt = tile * TC_P + p;
@@ -304,11 +313,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             const int m = l - 1;                                       // weight matrix index
             const int dout = lay.d[l];
             const int NF = (dout <= 16) ? 16 : 64;
-            {   // forward operand images of matrix m -> smem
-                const float4* src = reinterpret_cast<const float4*>(args.images + (size_t)m * TC_IMG_LAYER);
-                float4* dst = reinterpret_cast<float4*>(wimg);
-                for (int i = tid; i < TC_IMG_SET / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-            }
+            // operand images of matrix m (prefetched into registers one phase ahead) -> smem
+#pragma unroll
+            for (int i = 0; i < 9; ++i) reinterpret_cast<float4*>(wimg)[tid + i * TC_THREADS] = img[i];
             tm_wait_st();
             fence_async_smem();
             fence_before();
@@ -320,6 +327,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 mma_commit(bar_s);
             }
             TC_PROF(2);
+            {   // prefetch the next operand image while the MMAs run: forward image of the next matrix, or the adjoint image of the last one
+                const uint8_t* nsrc = (l < L) ? args.images + (size_t)(m + 1) * TC_IMG_LAYER : args.images + (size_t)m * TC_IMG_LAYER + TC_IMG_SET;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(nsrc) + tid + i * TC_THREADS);
+            }
             mbar_wait(bar_s, parity);
             parity ^= 1;
             fence_after();
@@ -387,11 +399,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
         for (int l = L; l >= 2; --l) {
             const int m = l - 1;
             const int din = lay.d[l - 1], dout = lay.d[l];
-            {   // adjoint operand images of matrix m -> smem
-                const float4* src = reinterpret_cast<const float4*>(args.images + (size_t)m * TC_IMG_LAYER + TC_IMG_SET);
-                float4* dst = reinterpret_cast<float4*>(wimg);
-                for (int i = tid; i < TC_IMG_SET / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) reinterpret_cast<float4*>(wimg)[tid + i * TC_THREADS] = img[i];     // adjoint image of matrix m
             tm_wait_st();
             fence_async_smem();
             fence_before();
@@ -403,6 +412,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 mma_commit(bar_s);
             }
             TC_PROF(7);
+            {   // prefetch: adjoint image of the next (shallower) matrix, or the first forward image of the next tile
+                const uint8_t* nsrc = (l > 2) ? args.images + (size_t)(m - 1) * TC_IMG_LAYER + TC_IMG_SET : args.images + (size_t)1 * TC_IMG_LAYER;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(nsrc) + tid + i * TC_THREADS);
+            }
             // ---- weight / bias gradient of layer l on the tensor cores (bf16 hi/mid operands, see above)
             const float* stash_in = stash + (size_t)(l - 2) * (TC_STASH_LAYER / 4);      // outputs of layer l-1 = inputs A of layer l
             const int NZ = (dout + 7) & ~7;                                              // N of the dW tile
@@ -466,14 +480,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     fence_after();
                     const uint32_t id = idesc_bf16_mn(64, NZ);
                     const uint32_t d = tbase + TM_LO;
-                    const uint32_t ahi = smem_u32(smem + DW_AHI), amid = smem_u32(smem + DW_AMID);
-                    const uint32_t zhi = smem_u32(smem + DW_ZHI), zmid = smem_u32(smem + DW_ZMID);
-#pragma unroll 1
-                    for (int s8 = 0; s8 < 8; ++s8) {     // 16 points per MMA
-                        const uint32_t o = (uint32_t)s8 * 256u;
-                        mma_bf16_ss(d, sdesc(ahi + o, 128, 2048), sdesc(zhi + o, 128, 2048), id, (k > 0 || s8 > 0) ? 1u : 0u);
-                        mma_bf16_ss(d, sdesc(ahi + o, 128, 2048), sdesc(zmid + o, 128, 2048), id, 1u);
-                        mma_bf16_ss(d, sdesc(amid + o, 128, 2048), sdesc(zhi + o, 128, 2048), id, 1u);
+                    const uint64_t ahi = sdesc(smem_u32(smem + DW_AHI), 128, 2048), amid = sdesc(smem_u32(smem + DW_AMID), 128, 2048);
+                    const uint64_t zhi = sdesc(smem_u32(smem + DW_ZHI), 128, 2048), zmid = sdesc(smem_u32(smem + DW_ZMID), 128, 2048);
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8) {     // 16 points per MMA: start address += 256 B
+                        const uint64_t o = (uint64_t)(s8 * 16);
+                        mma_bf16_ss(d, ahi + o, zhi + o, id, (k > 0 || s8 > 0) ? 1u : 0u);
+                        mma_bf16_ss(d, ahi + o, zmid + o, id, 1u);
+                        mma_bf16_ss(d, amid + o, zhi + o, id, 1u);
                     }
                     mma_commit(bar_s);
                 }
