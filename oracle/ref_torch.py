@@ -303,3 +303,46 @@ class Oracle:
         else:
             outs = (o[0], o[1], o[4], o[5], o[6]) + e
         return tuple(a.detach().numpy() for a in outs)
+
+
+# ----------------------------------------------------------------------------- plate pre-training losses
+def _net_cols(W, b, A, need_t=False):
+    A = _t(A)
+    x, y = A[:, 0:1], A[:, 1:2]
+    t = A[:, 2:3].clone().requires_grad_(need_t)
+    out = neural_net(torch.cat([x, y, t], 1), W, b)
+    return [out[:, i:i + 1] for i in range(out.shape[1])], t
+
+
+def loss_dist(dist_W, dist_b, DIST, IC):
+    """plate:194-200: fit of the distance-function net D to its targets + zero d/dt at the IC points
+    (net_dist plate:322-329, net_dist_dt plate:331-345).  Returns (loss, flat grad) with W, b lists of numpy arrays."""
+    W = [_t(w).clone().requires_grad_(True) for w in dist_W]
+    b = [_t(x).reshape(1, -1).clone().requires_grad_(True) for x in dist_b]
+    ms = lambda a: torch.mean(torch.square(a))
+    D, _ = _net_cols(W, b, DIST)
+    tg = _t(DIST)
+    loss = sum(ms(D[c] - tg[:, 3 + c:4 + c]) for c in range(5))
+    Di, t = _net_cols(W, b, IC, need_t=True)
+    loss = loss + ms(_grad(Di[0], t)) + ms(_grad(Di[1], t))
+    gs = torch.autograd.grad(loss, W + b)
+    return float(loss.detach()), np.concatenate([g.numpy().ravel() for g in gs])
+
+
+def loss_part(part_W, part_b, IC, LF, RT, UP, LW):
+    """plate:201-215 with net_part plate:347-356."""
+    W = [_t(w).clone().requires_grad_(True) for w in part_W]
+    b = [_t(x).reshape(1, -1).clone().requires_grad_(True) for x in part_b]
+    ms = lambda a: torch.mean(torch.square(a))
+    P, t = _net_cols(W, b, IC, need_t=True)
+    loss = sum(ms(P[c]) for c in range(5)) + ms(_grad(P[0], t)) + ms(_grad(P[1], t))
+    P, _ = _net_cols(W, b, LF)
+    loss = loss + ms(P[0]) + ms(P[4])
+    P, _ = _net_cols(W, b, RT)
+    loss = loss + ms(P[2] - _t(RT)[:, 3:4]) + ms(P[4])
+    P, _ = _net_cols(W, b, LW)
+    loss = loss + ms(P[1]) + ms(P[4])
+    P, _ = _net_cols(W, b, UP)
+    loss = loss + ms(P[3]) + ms(P[4])
+    gs = torch.autograd.grad(loss, W + b)
+    return float(loss.detach()), np.concatenate([g.numpy().ravel() for g in gs])

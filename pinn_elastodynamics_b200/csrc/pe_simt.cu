@@ -19,8 +19,8 @@
 // that 128-bit loads of 32 lanes are bank-conflict free); all hidden activations are stashed per CTA in a
 // global scratch that stays L2 resident (296 CTAs x 133 KB for the 5x50 net) and re-read by the reverse
 // sweep.  Weights are read through L1 with warp-uniform 64/128-bit __ldg.  Weight-gradient blocks are
-// accumulated over the tile in registers and added to the CTA's private partial buffer (plain
-// read-modify-write, fixed thread->element map: deterministic, no atomics); pe_reduce_* sums the slots.
+// accumulated over the tile in registers and added to the CTA's private partial buffer with red.global.add.v4.f32
+// (fire and forget; exactly one owner thread per element and tile => fixed order, deterministic); pe_reduce_* sums the slots.
 #include "pe_common.cuh"
 #include "pe_device.cuh"
 
@@ -313,16 +313,9 @@ resid_simt_kernel(const PeResidArgs args) {
                         const int i = i0 + r;
                         if (i < din) {
                             float* dstp = gW + (size_t)i * ldw + j0;
-                            if (j0 < ldw) {
-                                float4 v = __ldcg(reinterpret_cast<float4*>(dstp));
-                                v.x += acc[r][0]; v.y += acc[r][1]; v.z += acc[r][2]; v.w += acc[r][3];
-                                __stcg(reinterpret_cast<float4*>(dstp), v);
-                            }
-                            if (j0 + 4 < ldw) {
-                                float4 v = __ldcg(reinterpret_cast<float4*>(dstp + 4));
-                                v.x += acc[r][4]; v.y += acc[r][5]; v.z += acc[r][6]; v.w += acc[r][7];
-                                __stcg(reinterpret_cast<float4*>(dstp + 4), v);
-                            }
+                            // red.global.add.v4.f32 (no return value, nothing to wait for); one owner thread per element and tile => fixed order
+                            if (j0 < ldw) atomicAdd(reinterpret_cast<float4*>(dstp), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+                            if (j0 + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dstp + 4), make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
                         }
                     }
                 }
@@ -332,7 +325,7 @@ resid_simt_kernel(const PeResidArgs args) {
                     float s = 0.f;
 #pragma unroll 8
                     for (int pp = 0; pp < PE_P; ++pp) s += bufZ[pp * ldo + j];
-                    __stcg(gB + j, __ldcg(gB + j) + s);
+                    atomicAdd(gB + j, s);
                 }
             }
             if (l == 1) { __syncthreads(); break; }

@@ -148,11 +148,14 @@ class _Base:
         return [(int(i * N / batch_num), int((i + 1) * N / batch_num)) for i in range(batch_num)]
 
     # ---- L-BFGS-B through SciPy, as tf.contrib.opt.ScipyOptimizerInterface does (plate:240-247,522-525)
-    def _bfgs(self, options, callback, engine=None, net=None, total=None):
+    def _bfgs(self, options, callback, engine=None, net=None, total=None, shown=None):
+        """total(terms) is the minimised scalar; shown(terms) is what the reference passes to loss_callback
+        (`fetches`, e.g. the unscaled loss_DIST while 1000*loss_DIST is minimised, plate:220,543)."""
         import scipy.optimize
         engine = engine or self.engine
         net = net or self.uv_net
         total = total or self._total
+        shown = shown or total
 
         def fun(x):
             net.set_flat(x)
@@ -160,7 +163,7 @@ class _Base:
             terms = engine.terms_host()
             g = engine.grad_compact_host().astype(np.float64)
             f = total(terms)
-            callback(f)                                   # loss_callback fires on every evaluation (plate:463-465)
+            callback(shown(terms))                        # loss_callback fires on every evaluation (plate:463-465)
             return f, g
 
         x0 = net.get_flat().astype(np.float64)
@@ -246,6 +249,45 @@ class PINN(_Base):
         self._hole_term = eng.add_term('HOLE', L.RES_TRACTION, 1, self.HOLE[:, :3], terms=(2,), weights=(10.0,),
                                        aux=aux_h, aux_k=1 if self.composite else 0, **mat)
 
+    # ---- pre-training of the distance-function / particular-solution networks (plate:194-237, 527-559)
+    def _pre_engines(self):
+        if hasattr(self, 'dist_engine'):
+            return
+        if not self.composite or any(a is None for a in (self.IC, self.LF, self.RT, self.UP, self.LW, self.DIST)):
+            raise L.PeError('train_bfgs_dist / train_bfgs_part need dist/part networks and the IC, LF, RT, UP, LW, DIST point sets')
+        W = 1000.0                                                             # optimizer_dist / optimizer_part minimise 1000 * loss
+        de = self.dist_engine = LossEngine(self.dist_net, 'simt')
+        de.add_term('DIST', L.RES_COLS, 1, self.DIST[:, :8], cols=(0, 1, 2, 3, 4), tgts=(3, 4, 5, 6, 7), terms=(0,) * 5, weights=(W,) * 5)   # plate:194-198
+        de.add_term('IC_dt', L.RES_DT, 2, self.IC[:, :3], cols=(0, 1), tgts=(-1, -1), terms=(0, 0), weights=(W, W))                          # plate:199-200
+        pe_ = self.part_engine = LossEngine(self.part_net, 'simt')
+        pe_.add_term('IC', L.RES_COLS, 1, self.IC[:, :3], cols=(0, 1, 2, 3, 4), tgts=(-1,) * 5, terms=(0,) * 5, weights=(W,) * 5)            # plate:201-205
+        pe_.add_term('IC_dt', L.RES_DT, 2, self.IC[:, :3], cols=(0, 1), tgts=(-1, -1), terms=(0, 0), weights=(W, W))                         # plate:206-207
+        pe_.add_term('LF', L.RES_COLS, 1, self.LF[:, :3], cols=(0, 4), tgts=(-1, -1), terms=(0, 0), weights=(W, W))                          # plate:208-209
+        pe_.add_term('RT', L.RES_COLS, 1, self.RT[:, :4], cols=(2, 4), tgts=(3, -1), terms=(0, 0), weights=(W, W))                           # plate:210-211
+        pe_.add_term('LW', L.RES_COLS, 1, self.LW[:, :3], cols=(1, 4), tgts=(-1, -1), terms=(0, 0), weights=(W, W))                          # plate:212-213
+        pe_.add_term('UP', L.RES_COLS, 1, self.UP[:, :3], cols=(3, 4), tgts=(-1, -1), terms=(0, 0), weights=(W, W))                          # plate:214-215
+
+    def callback_dist(self, loss_dist):
+        self.count = self.count + 1
+        if self.verbose:
+            print('{} th iterations, Loss: {}'.format(self.count, loss_dist))
+
+    callback_part = callback_dist
+
+    def train_bfgs_dist(self, options=None):
+        self._pre_engines()
+        r = self._bfgs(options or self.pre_options, self.callback_dist, engine=self.dist_engine, net=self.dist_net,
+                       total=lambda t: 1000.0 * t[0], shown=lambda t: t[0])
+        self.refresh_composite()
+        return r
+
+    def train_bfgs_part(self, options=None):
+        self._pre_engines()
+        r = self._bfgs(options or self.pre_options, self.callback_part, engine=self.part_engine, net=self.part_net,
+                       total=lambda t: 1000.0 * t[0], shown=lambda t: t[0])
+        self.refresh_composite()
+        return r
+
     def refresh_composite(self):
         """Re-evaluate the frozen dist/part jets (after train_bfgs_dist / train_bfgs_part changed them)."""
         if self.composite:
@@ -278,8 +320,15 @@ class PINN(_Base):
     def getloss(self):
         t = self._evaluate_terms()
         vals = {'loss_f_uv': t[0], 'loss_f_s': t[1], 'loss_HOLE': t[2], 'loss': self._total(t)}
-        for k in ('loss_f_uv', 'loss_f_s', 'loss_HOLE', 'loss'):
-            print(k, vals[k])
+        try:                                                                   # plate:605-606
+            self._pre_engines()
+            self.part_engine.evaluate(); vals['loss_PART'] = self.part_engine.terms_host()[0]
+            self.dist_engine.evaluate(); vals['loss_DIST'] = self.dist_engine.terms_host()[0]
+        except L.PeError:
+            pass
+        for k in ('loss_f_uv', 'loss_f_s', 'loss_HOLE', 'loss', 'loss_PART', 'loss_DIST'):
+            if k in vals:
+                print(k, vals[k])
         return vals
 
 

@@ -337,3 +337,54 @@ def test_tc_fast_mode_is_tf32_accurate(pe, golden):
     np.testing.assert_allclose(t[:2], g["f5_terms"][:2], rtol=3e-2)
     errs = per_layer_grad_err(m.engine.grad_compact_host(), g['f5_grad'], layers)
     assert max(e for _, e in errs) <= 1e-1, errs
+
+
+# ------------------------------------------------------------------------------ plate pre-training
+def _plate_sets(rng):
+    lb, ub = np.array([0, 0, 0.]), np.array([.5, .5, 10.])
+    U = lambda n: rng.uniform(lb, ub, (n, 3))
+    IC = U(90); IC[:, 2] = 0
+    LF = U(70); LF[:, 0] = 0
+    RT = U(110); RT[:, 0] = .5; RT = np.concatenate([RT, 0.5 * np.sin(2 * np.pi * RT[:, 2:3] / 5 + 1.5 * np.pi) + 0.5], 1)
+    UP = U(60); UP[:, 1] = .5
+    LW = U(50); LW[:, 1] = 0
+    D = U(333); DIST = np.concatenate([D, rng.uniform(0, .3, (333, 5))], 1)
+    return IC, LF, RT, UP, LW, DIST
+
+
+def test_plate_pretraining_losses_and_lbfgs(pe, golden):
+    """loss_DIST / loss_PART (plate:194-215), their gradients, and train_bfgs_dist / train_bfgs_part (plate:527-559)"""
+    g = golden('plate_ckpt.npz')
+    di, pa = unpack_golden(g, 'dist'), unpack_golden(g, 'part')
+    rng = np.random.default_rng(12)
+    IC, LF, RT, UP, LW, DIST = _plate_sets(rng)
+    uv_layers = [3, 20, 20, 5]
+    Collo, HOLE = g['collo'][:200], g['hole'][:40]
+    m = pe.PINN(Collo, HOLE, IC, LF, RT, UP, LW, DIST, uv_layers, layers_of(di[0]), layers_of(pa[0]), None, None, verbose=False)
+    Wd, bd = R.xavier_params(layers_of(di[0]), seed=31); bd = random_biases(bd, 1)
+    Wp, bp = R.xavier_params(layers_of(pa[0]), seed=32); bp = random_biases(bp, 2)
+    m.dist_net.set_weights(Wd, bd); m.part_net.set_weights(Wp, bp); m.refresh_composite()
+    m._pre_engines()
+    ld, gd = R.loss_dist(Wd, bd, DIST, IC)
+    lp, gp = R.loss_part(Wp, bp, IC, LF, RT, UP, LW)
+    m.dist_engine.evaluate(); m.part_engine.evaluate()
+    assert m.dist_engine.terms_host()[0] == pytest.approx(ld, rel=1e-5)
+    assert m.part_engine.terms_host()[0] == pytest.approx(lp, rel=1e-5)
+    assert rel_err(m.dist_engine.grad_compact_host(), 1000 * gd) <= 3e-5
+    assert rel_err(m.part_engine.grad_compact_host(), 1000 * gp) <= 3e-5
+    # L-BFGS pre-training reduces both and the composite residual graph picks the new nets up
+    shown = []
+    m.callback_dist = lambda l: shown.append(l)
+    m.train_bfgs_dist(dict(maxiter=30, maxfun=40, maxcor=50, maxls=50, ftol=1e-5 * np.finfo(float).eps))
+    assert shown[0] == pytest.approx(ld, rel=1e-4) and shown[-1] < 0.5 * shown[0]
+    shown2 = []
+    m.callback_part = lambda l: shown2.append(l)
+    m.train_bfgs_part(dict(maxiter=30, maxfun=40, maxcor=50, maxls=50, ftol=1e-5 * np.finfo(float).eps))
+    assert shown2[-1] < 0.5 * shown2[0]
+    Wd2, bd2 = m.dist_net.get_weights(np.float64); Wp2, bp2 = m.part_net.get_weights(np.float64)
+    Wu, bu = m.uv_net.get_weights(np.float64)
+    orc = R.Oracle('plate', Wu, bu, dist=(Wd2, bd2), part=(Wp2, bp2))
+    T, loss, gref = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
+    _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, uv_layers, 2e-5, 1e-4)
+    vals = m.getloss()
+    assert 'loss_PART' in vals and 'loss_DIST' in vals
