@@ -36,7 +36,8 @@ extern "C" {
 #define PE_MAX_LAYERS 16        /* weight matrices per network */
 #define PE_MAX_TERMS 8          /* loss-term accumulators per model (loss_f_uv, loss_f_s, loss_IC, ...) */
 #define PE_MAX_COLS 8           /* residual columns of one data term */
-#define PE_TILE_POINTS 32       /* points per CTA tile (one warp lane per point) */
+#define PE_TILE_POINTS 32       /* points per CTA tile of the SIMT engine (one warp lane per point) */
+#define PE_TC_TILE 128           /* points per CTA tile of the tensor-core engines (UMMA M) */
 
 /* residual kinds (what the point set contributes to the loss) */
 enum {
@@ -120,6 +121,18 @@ int pe_residual_loss_grad(const pe_plan *plan, const pe_term_desc *term, int K, 
                           const float *d_params,
                           float *d_grad_partials, float *d_term_partials, float *d_stash,
                           int slot_base, void *stream);
+
+/* Tensor-core engines only.  pe_residual_loss_grad for the F5 collocation set plus a SECOND, primal-only point set
+ * (PE_RES_TRACTION, plate:452-461, or PE_RES_COLS; K = 1) processed by the same launch as extra 128-point tiles: its value
+ * stream rides the K = 5 tiles and the derivative streams get zero seeds.  Saves one latency-bound launch per step (the
+ * extra tiles usually disappear in the tail of the persistent grid).  Slots / scratch: query pe_plan_slots /
+ * pe_plan_scratch_floats with n_points = PE_TC_TILE * (ceil(n/PE_TC_TILE) + ceil(n2/PE_TC_TILE)). */
+int pe_residual_loss_grad_fused(const pe_plan *plan, const pe_term_desc *term, int K, int engine,
+                                const float *d_points, int n_local, const float *d_aux,
+                                const pe_term_desc *term2, const float *d_points2, int n2_local, const float *d_aux2,
+                                const float *d_params,
+                                float *d_grad_partials, float *d_term_partials, float *d_stash,
+                                int slot_base, void *stream);
 
 /* Deterministic fixed-order sum over slots: d_out[0..Pp) = sum_s partials[s], d_out[Pp..Pp+PE_MAX_TERMS) =
  * sum_s term partials.  d_out is the buffer a multi-GPU caller all-reduces.  If d_terms_copy is

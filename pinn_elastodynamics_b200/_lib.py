@@ -17,6 +17,7 @@ PE_MAX_LAYERS = 16
 PE_MAX_TERMS = 8
 PE_MAX_COLS = 8
 PE_TILE_POINTS = 32
+PE_TC_TILE = 128
 
 RES_F5, RES_F7, RES_COLS, RES_TRACTION, RES_DT = 0, 1, 2, 3, 4
 ENGINE_SIMT_FP32, ENGINE_TC_TF32X3, ENGINE_TC_TF32 = 0, 1, 2
@@ -54,6 +55,7 @@ SYMBOLS = [
     ('pe_pack_params', _i, [_vp, _vp, _vp]),
     ('pe_unpack_params', _i, [_vp, _vp, _vp]),
     ('pe_residual_loss_grad', _i, [_vp, C.POINTER(TermDesc), _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    ('pe_residual_loss_grad_fused', _i, [_vp, C.POINTER(TermDesc), _i, _i, _vp, _i, _vp, C.POINTER(TermDesc), _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     ('pe_reduce_partials', _i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     ('pe_adam_step', _i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     ('pe_reduce_adam', _i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),

@@ -15,7 +15,8 @@ void pe_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st);
+int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st,
+                       const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 int pe_tc_supported(const pe_plan* plan, int K, int engine);
 int pe_tc_slots(const pe_plan* plan, int n_points);
 size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
@@ -184,11 +185,11 @@ static int check_term(const pe_plan* plan, const pe_term_desc* t, int K) {
     return 0;
 }
 
-extern "C" int pe_residual_loss_grad(const pe_plan* plan, const pe_term_desc* term, int K, int engine,
-                                     const float* d_points, int n_local, const float* d_aux,
-                                     const float* d_params,
-                                     float* d_grad_partials, float* d_term_partials, float* d_stash,
-                                     int slot_base, void* stream) {
+static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K, int engine,
+                           const float* d_points, int n_local, const float* d_aux,
+                           const pe_term_desc* term2, const float* d_points2, int n2_local, const float* d_aux2,
+                           const float* d_params, float* d_grad_partials, float* d_term_partials, float* d_stash,
+                           int slot_base, void* stream) {
     if (!plan || !term) { pe_set_error("null plan/term"); return 1; }
     if (plan->device < 0) { pe_set_error("plan was created without a device"); return 1; }
     if (check_term(plan, term, K)) return 1;
@@ -207,14 +208,43 @@ extern "C" int pe_residual_loss_grad(const pe_plan* plan, const pe_term_desc* te
     a.slot_base = slot_base;
     a.stash_floats = (int)simt_stash_floats_per_slot(plan, K);
     a.inv_n = 1.0f / (float)term->n_global;
-    int slots = pe_plan_slots(plan, n_local, K, engine);
-    if (engine == PE_ENGINE_SIMT_FP32) return pe_launch_resid_simt(plan, a, K, slots, (cudaStream_t)stream);
+    if (engine == PE_ENGINE_SIMT_FP32) {
+        if (term2) { pe_set_error("fused point sets need a tensor-core engine"); return 1; }
+        return pe_launch_resid_simt(plan, a, K, pe_plan_slots(plan, n_local, K, engine), (cudaStream_t)stream);
+    }
     if (engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32) {
         if (!pe_engine_supported(plan, term->kind, K, engine)) { pe_set_error("tensor-core engine does not support this residual kind / network (F5, K=5, hidden widths <= 56)"); return 1; }
-        return pe_launch_resid_tc(plan, a, K, engine, slots, (cudaStream_t)stream);
+        int n_eff = n_local;
+        if (term2) {
+            if (check_term(plan, term2, 1)) return 1;
+            if (term2->kind != PE_RES_TRACTION && term2->kind != PE_RES_COLS) { pe_set_error("fused set must be PE_RES_TRACTION or PE_RES_COLS"); return 1; }
+            if (term2->aux_k && !d_aux2) { pe_set_error("fused composite set needs d_aux2"); return 1; }
+            n_eff = PE_TC_TILE * ((n_local + PE_TC_TILE - 1) / PE_TC_TILE + (n2_local + PE_TC_TILE - 1) / PE_TC_TILE);
+        }
+        return pe_launch_resid_tc(plan, a, K, engine, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
     }
     pe_set_error("unknown engine %d", engine);
     return 1;
+}
+
+extern "C" int pe_residual_loss_grad(const pe_plan* plan, const pe_term_desc* term, int K, int engine,
+                                     const float* d_points, int n_local, const float* d_aux,
+                                     const float* d_params,
+                                     float* d_grad_partials, float* d_term_partials, float* d_stash,
+                                     int slot_base, void* stream) {
+    return residual_common(plan, term, K, engine, d_points, n_local, d_aux, nullptr, nullptr, 0, nullptr,
+                           d_params, d_grad_partials, d_term_partials, d_stash, slot_base, stream);
+}
+
+extern "C" int pe_residual_loss_grad_fused(const pe_plan* plan, const pe_term_desc* term, int K, int engine,
+                                           const float* d_points, int n_local, const float* d_aux,
+                                           const pe_term_desc* term2, const float* d_points2, int n2_local, const float* d_aux2,
+                                           const float* d_params,
+                                           float* d_grad_partials, float* d_term_partials, float* d_stash,
+                                           int slot_base, void* stream) {
+    if (!term2) { pe_set_error("null term2"); return 1; }
+    return residual_common(plan, term, K, engine, d_points, n_local, d_aux, term2, d_points2, n2_local, d_aux2,
+                           d_params, d_grad_partials, d_term_partials, d_stash, slot_base, stream);
 }
 
 extern "C" int pe_forward_fields(const pe_plan* plan, int formulation, const float* d_points, int ld, int n,

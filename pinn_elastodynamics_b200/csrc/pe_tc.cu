@@ -30,6 +30,7 @@
 // on the FFMA pipe (8x8 register blocks, contraction split over 4 point-quarters inside a warp, shuffle-reduced)
 // concurrently with the asynchronous adjoint MMAs of the same layer.
 #include <cuda_bf16.h>
+#include <cstring>
 #include "pe_common.cuh"
 #include "pe_device.cuh"
 
@@ -142,6 +143,12 @@ struct TcArgs {
     PeResidArgs r;
     const uint8_t* images;
     int fast;            // 1 = single-pass TF32
+    // optional second, primal-only point set (traction / data term, K = 1) fused into the same launch as extra tiles
+    pe_term_desc term2;
+    const float* points2;
+    const float* aux2;
+    int n2;
+    float inv_n2;
     unsigned long long* prof;   // optional: 16 phase-cycle counters written by CTA 0 / thread 0 (pe_debug_set_tc_profile)
 };
 
@@ -262,16 +269,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     float4 img[9];                                   // one operand-image set (36,864 B / 256 threads), prefetched a phase ahead
 #pragma unroll
     for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(args.images + (size_t)1 * TC_IMG_LAYER) + tid + i * TC_THREADS);
-    const int ntiles = (A.n + TC_P - 1) / TC_P;
+    const pe_term_desc& T2 = args.term2;
+    float tsum2[PE_MAX_TERMS];
+#pragma unroll
+    for (int i = 0; i < PE_MAX_TERMS; ++i) tsum2[i] = 0.f;
+    const int ntiles_main = (A.n + TC_P - 1) / TC_P;
+    const int ntiles = ntiles_main + (args.n2 + TC_P - 1) / TC_P;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int pt = tile * TC_P + p;
-        const bool valid = pt < A.n;
-        const float* row = A.points + (size_t)(valid ? pt : 0) * T.ld;
+        const bool sec = tile >= ntiles_main;                          // tile of the fused primal-only set (CTA-uniform)
+        const pe_term_desc& Tc = sec ? T2 : T;
+        const int pt = (sec ? tile - ntiles_main : tile) * TC_P + p;
+        const bool valid = pt < (sec ? args.n2 : A.n);
+        const float* row = (sec ? args.points2 : A.points) + (size_t)(valid ? pt : 0) * Tc.ld;
         if (h == 0) {
             float x = 0.f, y = 0.f, t = 0.f;
             if (valid) { x = row[0]; y = row[1]; t = row[2]; }
-            *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(fmaf(x, T.in_scale[0], T.in_shift[0]), fmaf(y, T.in_scale[1], T.in_shift[1]),
-                                                                    fmaf(t, T.in_scale[2], T.in_shift[2]), valid ? 1.f : 0.f);
+            *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(fmaf(x, Tc.in_scale[0], Tc.in_shift[0]), fmaf(y, Tc.in_scale[1], Tc.in_shift[1]),
+                                                                    fmaf(t, Tc.in_scale[2], Tc.in_shift[2]), valid ? 1.f : 0.f);
         }
         __syncthreads();
         TC_PROF(15);
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     if (j < dout) {
                         const float w0 = __ldg(W0 + j), w1 = __ldg(W0 + ldw + j), w2 = __ldg(W0 + 2 * ldw + j);
                         z[0] = fmaf(c4.x, w0, fmaf(c4.y, w1, c4.z * w2));
-                        z[1] = T.in_scale[0] * w0; z[2] = T.in_scale[1] * w1; z[3] = T.in_scale[2] * w2; z[4] = 0.f;
+                        z[1] = Tc.in_scale[0] * w0; z[2] = Tc.in_scale[1] * w1; z[3] = Tc.in_scale[2] * w2; z[4] = 0.f;
                         act_fwd<5>(z, __ldg(b0 + j));
                     }
 #pragma unroll
@@ -381,8 +395,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 }
 #pragma unroll
                 for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += __ldg(bias + u);
-                const float* aux_row = A.aux ? A.aux + (size_t)(valid ? pt : 0) * 50 : nullptr;
-                residual_stage<5>(Y, T, aux_row, row, valid, A.inv_n, tsum);
+                if (!sec) {
+                    const float* aux_row = A.aux ? A.aux + (size_t)(valid ? pt : 0) * 50 : nullptr;
+                    residual_stage<5>(Y, T, aux_row, row, valid, A.inv_n, tsum);
+                } else {    // primal-only set: residual on the value stream, zero seeds for the derivative streams
+                    float Y1[1][PE_UJ];
+#pragma unroll
+                    for (int u = 0; u < PE_UJ; ++u) Y1[0][u] = Y[0][u];
+                    const float* aux_row = args.aux2 ? args.aux2 + (size_t)(valid ? pt : 0) * 10 : nullptr;
+                    residual_stage<1>(Y1, T2, aux_row, row, valid, args.inv_n2, tsum2);
+#pragma unroll
+                    for (int u = 0; u < PE_UJ; ++u) {
+                        Y[0][u] = Y1[0][u];
+#pragma unroll
+                        for (int k = 1; k < 5; ++k) Y[k][u] = 0.f;
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     const float4 v0 = make_float4(Y[k][0], Y[k][1], Y[k][2], Y[k][3]);
@@ -580,9 +608,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     const float zx = *reinterpret_cast<const float*>(base + 1 * TC_ACT_STREAM + pp * 16);
                     const float zy = *reinterpret_cast<const float*>(base + 2 * TC_ACT_STREAM + pp * 16);
                     const float zt = *reinterpret_cast<const float*>(base + 3 * TC_ACT_STREAM + pp * 16);
-                    g0 = fmaf(c4.x, zv, fmaf(T.in_scale[0], zx, g0));
-                    g1 = fmaf(c4.y, zv, fmaf(T.in_scale[1], zy, g1));
-                    g2 = fmaf(c4.z, zv, fmaf(T.in_scale[2], zt, g2));
+                    g0 = fmaf(c4.x, zv, fmaf(Tc.in_scale[0], zx, g0));
+                    g1 = fmaf(c4.y, zv, fmaf(Tc.in_scale[1], zy, g1));
+                    g2 = fmaf(c4.z, zv, fmaf(Tc.in_scale[2], zt, g2));
                     gb += zv;
                 }
             }
@@ -609,21 +637,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     TC_PROF(14);
     if (args.prof && blockIdx.x == 0 && tid == 0)
         for (int i = 0; i < 16; ++i) atomicAdd(args.prof + i, prof_acc[i]);
-    // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem
+    // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem (fixed order)
     {
-        float tot[2];
+        float tot[2 + PE_MAX_TERMS];
         tot[0] = warp_sum(tsum[0]);
         tot[1] = warp_sum(tsum[1]);
+#pragma unroll
+        for (int c = 0; c < PE_MAX_TERMS; ++c) tot[2 + c] = warp_sum(tsum2[c]);
         __syncthreads();
-        if (h == 0 && lane == 0) { red[2 * warp] = tot[0]; red[2 * warp + 1] = tot[1]; }
+        if (h == 0 && lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 2 + PE_MAX_TERMS; ++c) red[(2 + PE_MAX_TERMS) * warp + c] = tot[c];
+        }
         __syncthreads();
         if (tid == 0) {
             float* tp = A.term_partials + (size_t)slot * PE_MAX_TERMS;
 #pragma unroll
             for (int i = 0; i < PE_MAX_TERMS; ++i) tp[i] = 0.f;
-            float s0 = red[0] + red[2] + red[4] + red[6], s1 = red[1] + red[3] + red[5] + red[7];
-            tp[T.term[0]] += s0 * A.inv_n;
-            tp[T.term[1]] += s1 * A.inv_n;
+            auto S = [&](int c) { const int st = 2 + PE_MAX_TERMS; return red[c] + red[st + c] + red[2 * st + c] + red[3 * st + c]; };
+            tp[T.term[0]] += S(0) * A.inv_n;
+            tp[T.term[1]] += S(1) * A.inv_n;
+            if (args.n2 > 0) {
+                const int nres2 = (T2.kind == PE_RES_TRACTION) ? 1 : T2.ncols;
+                for (int c = 0; c < nres2; ++c) tp[T2.term[c]] += S(2 + c) * args.inv_n2;
+            }
         }
     }
     fence_before();
@@ -642,7 +679,7 @@ int pe_tc_supported(const pe_plan* plan, int K, int engine) {
     return 1;
 }
 
-int pe_tc_slots(const pe_plan* plan, int n_points) {
+int pe_tc_slots(const pe_plan* plan, int n_points) {      // for a fused launch pass 128 * (tiles of set 1 + tiles of set 2)
     int ntiles = (n_points + TC_P - 1) / TC_P;
     int s = ntiles < plan->sms ? ntiles : plan->sms;
     return s < 1 ? 1 : s;
@@ -654,11 +691,18 @@ size_t pe_tc_image_floats(const pe_plan* plan) { return (size_t)plan->lay.L * (T
 static unsigned long long* g_tc_prof = nullptr;
 extern "C" void pe_debug_set_tc_profile(unsigned long long* d_counters16) { g_tc_prof = d_counters16; }
 
-int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st) {
+int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st,
+                       const pe_term_desc* term2, const float* points2, int n2, const float* aux2) {
     (void)K;
     TcArgs t;
     t.r = a;
     t.prof = g_tc_prof;
+    t.n2 = 0; t.points2 = nullptr; t.aux2 = nullptr; t.inv_n2 = 0.f;
+    memset(&t.term2, 0, sizeof(t.term2));
+    if (term2 && n2 > 0) {
+        t.term2 = *term2; t.points2 = points2; t.n2 = n2; t.aux2 = term2->aux_k ? aux2 : nullptr;
+        t.inv_n2 = 1.0f / (float)term2->n_global;
+    }
     t.fast = (engine == PE_ENGINE_TC_TF32) ? 1 : 0;
     // scratch layout: [slots x stash floats][weight images]
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);

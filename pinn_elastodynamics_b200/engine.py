@@ -201,13 +201,27 @@ class LossEngine:
     def build(self):
         base, stash = 0, 1
         for t in self.terms:
-            n = t.hi - t.lo
+            t.fused_into, t.fused = None, None
             # the requested engine where it implements the term, the fp32 SIMT engine elsewhere (data / boundary terms)
             t.engine = self.engine if self.lib.pe_engine_supported(self.net.plan, t.kind, t.K, self.engine) else L.ENGINE_SIMT_FP32
-            t.slots = self.lib.pe_plan_slots(self.net.plan, max(n, 1), t.K, t.engine)
+        # tensor-core engine: one primal-only set (hole traction / data term) rides the collocation launch as extra tiles
+        main = next((t for t in self.terms if t.enabled and t.engine != L.ENGINE_SIMT_FP32), None)
+        if main is not None:
+            sec = next((t for t in self.terms if t.enabled and t is not main and t.K == 1 and t.kind in (L.RES_TRACTION, L.RES_COLS)), None)
+            if sec is not None:
+                main.fused, sec.fused_into = sec, main
+        for t in self.terms:
+            if t.fused_into is not None:
+                t.slots, t.slot_base = 0, base
+                continue
+            n = max(t.hi - t.lo, 1)
+            if t.fused is not None:
+                tiles = -(-n // L.PE_TC_TILE) + -(-max(t.fused.hi - t.fused.lo, 1) // L.PE_TC_TILE)
+                n = tiles * L.PE_TC_TILE
+            t.slots = self.lib.pe_plan_slots(self.net.plan, n, t.K, t.engine)
             t.slot_base = base
             base += t.slots
-            stash = max(stash, self.lib.pe_plan_scratch_floats(self.net.plan, max(n, 1), t.K, t.engine))
+            stash = max(stash, self.lib.pe_plan_scratch_floats(self.net.plan, n, t.K, t.engine))
         self.n_slots = base
         need = base * self.net.Pp
         if not hasattr(self, 'gpart') or self.gpart.numel() < need:
@@ -227,7 +241,7 @@ class LossEngine:
         st = self._stream()
         slots = 0
         for t in self.terms:
-            if not t.enabled:
+            if not t.enabled or t.fused_into is not None:
                 continue
             n = t.hi - t.lo
             pts = t.points[t.lo:t.hi] if (t.lo, t.hi) != (0, t.points.shape[0]) else t.points
@@ -235,10 +249,17 @@ class LossEngine:
             if self.kernel_events is not None:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            L.check(self.lib.pe_residual_loss_grad(self.net.plan, C.byref(t.desc), t.K, t.engine,
-                                                   _ptr(pts), n, _ptr(aux), _ptr(self.net.params),
-                                                   _ptr(self.gpart), _ptr(self.tpart), _ptr(self.stash), slots, st),
-                    f'pe_residual_loss_grad[{t.name}]')
+            if t.fused is not None:
+                f = t.fused
+                L.check(self.lib.pe_residual_loss_grad_fused(self.net.plan, C.byref(t.desc), t.K, t.engine, _ptr(pts), n, _ptr(aux),
+                                                             C.byref(f.desc), _ptr(f.points[f.lo:f.hi]), f.hi - f.lo, _ptr(None if f.aux is None else f.aux[f.lo:f.hi]),
+                                                             _ptr(self.net.params), _ptr(self.gpart), _ptr(self.tpart), _ptr(self.stash), slots, st),
+                        f'pe_residual_loss_grad_fused[{t.name}+{f.name}]')
+            else:
+                L.check(self.lib.pe_residual_loss_grad(self.net.plan, C.byref(t.desc), t.K, t.engine,
+                                                       _ptr(pts), n, _ptr(aux), _ptr(self.net.params),
+                                                       _ptr(self.gpart), _ptr(self.tpart), _ptr(self.stash), slots, st),
+                        f'pe_residual_loss_grad[{t.name}]')
             if self.kernel_events is not None:
                 e1.record()
                 self.kernel_events.setdefault(t.name, []).append((e0, e1))

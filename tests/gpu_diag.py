@@ -34,6 +34,7 @@ print('grad per-layer rel err', per_layer_grad_err(gc, gref, layers))
 # only collocation term / only hole term
 for name in ('Collo', 'HOLE'):
     for tm in m.engine.terms: tm.enabled = (tm.name == name)
+    m.engine._built = False
     m.engine.evaluate(); gc = m.engine.grad_compact_host(); tt = m.engine.terms_host()
     Tt, _ = orc.loss_terms(sets)
     l = 10 * (Tt['loss_f_uv'] + Tt['loss_f_s']) if name == 'Collo' else 10 * Tt['loss_HOLE']
@@ -41,6 +42,7 @@ for name in ('Collo', 'HOLE'):
     gr = np.concatenate([x.numpy().ravel() for x in gs])
     print(name, 'terms', tt[:3], 'grad err', per_layer_grad_err(gc, gr, layers))
 for tm in m.engine.terms: tm.enabled = True
+m.engine._built = False
 # 3. timing at 50k points
 rng = np.random.default_rng(0)
 N = 50000
