@@ -116,22 +116,51 @@ class _Base:
         eng = self.engine
         self.h2d_bytes_per_step = self.d2h_bytes_per_step = 0
         if refeed:
-            pinned = [(t, t.points.cpu().pin_memory()) for t in eng.terms if t.enabled]
-            self.h2d_bytes_per_step = sum(h.numel() * 4 for _, h in pinned)
-            host_row = torch.zeros(L.PE_MAX_TERMS, dtype=torch.float32).pin_memory()
-            self.d2h_bytes_per_step = host_row.numel() * 4
+            # double-buffered device copies of every point set + a copy stream: the upload of step i+1 overlaps the
+            # kernels of step i; the loss terms of step i-1 are read back while step i runs (queue stays 1-2 steps deep)
+            terms = [t for t in eng.terms if t.enabled]
+            pinned = [t.points.cpu().pin_memory() for t in terms]
+            bufs = [(t.points, torch.empty_like(t.points)) for t in terms]
+            self.h2d_bytes_per_step = sum(h.numel() * 4 for h in pinned)
+            host_rows = torch.zeros((2, L.PE_MAX_TERMS), dtype=torch.float32).pin_memory()
+            self.d2h_bytes_per_step = L.PE_MAX_TERMS * 4
+            copy_stream = torch.cuda.Stream(self.device)
+            main = torch.cuda.current_stream(self.device)
+            up_done = [torch.cuda.Event(), torch.cuda.Event()]          # upload into buffer b finished
+            used_done = [torch.cuda.Event(), torch.cuda.Event()]        # kernels reading buffer b finished
+            step_done = [torch.cuda.Event(), torch.cuda.Event()]        # loss row of this parity copied to the host
+
+            def upload(b):
+                copy_stream.wait_event(used_done[b])
+                with torch.cuda.stream(copy_stream):
+                    for t, h, bb in zip(terms, pinned, bufs):
+                        bb[b].copy_(h, non_blocking=True)
+                    up_done[b].record(copy_stream)
+            used_done[0].record(main); used_done[1].record(main)
+            upload(0)
         for (a, b) in chunks:
             if a is not None:
                 eng.set_chunk(self._collo_term, a, b)
             hist = torch.zeros((iters + 1, L.PE_MAX_TERMS), dtype=torch.float32, device=self.device)
             for it in range(iters):
                 if refeed:
-                    for t, h in pinned:
-                        t.points.copy_(h, non_blocking=True)
+                    cur = it & 1
+                    main.wait_event(up_done[cur])
+                    for t, bb in zip(terms, bufs):
+                        t.points = bb[cur]
+                    if it + 1 < iters:
+                        upload(1 - cur)
                 eng.adam_step(learning_rate, hist[it])                 # hist[it] = terms BEFORE update it
                 if refeed:
-                    host_row.copy_(hist[it], non_blocking=True)
-                    torch.cuda.current_stream(self.device).synchronize()
+                    used_done[cur].record(main)
+                    host_rows[cur].copy_(hist[it], non_blocking=True)
+                    step_done[cur].record(main)
+                    if it > 0:
+                        step_done[1 - cur].synchronize()               # loss of the previous step is on the host
+            if refeed:
+                torch.cuda.current_stream(self.device).synchronize()
+                for t, bb in zip(terms, bufs):
+                    t.points = bb[0]
             eng.evaluate(hist[iters])                                  # terms after the last update
             h = hist.cpu().numpy().astype(np.float64)
             if self.verbose:                                           # same lines as plate:499-501, printed after the

@@ -388,3 +388,16 @@ def test_plate_pretraining_losses_and_lbfgs(pe, golden):
     _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, uv_layers, 2e-5, 1e-4)
     vals = m.getloss()
     assert 'loss_PART' in vals and 'loss_DIST' in vals
+
+
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_refeed_path_equals_resident_path(pe, golden, engine):
+    """train(refeed=True) (bench `e2e`: per-step host->device re-upload, pipelined through two device buffers, loss read back
+    every step) must produce exactly the same trajectory as the resident path."""
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    a = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine).train(7, 5e-4)
+    b = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine).train(7, 5e-4, refeed=True)
+    for x, y in zip(a, b):
+        assert x == y
