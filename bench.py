@@ -34,6 +34,9 @@ LAYERS = [3] + 5 * [50] + [5]
 S_WEIGHTS = sum(LAYERS[i] * LAYERS[i + 1] for i in range(len(LAYERS) - 1))     # 10,400
 FLOP_PER_POINT = 6 * 5 * S_WEIGHTS                                            # 6*K*S = 312,000
 METRIC = 'collocation-pt residual+grad evals/sec per Adam step'
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures of
+# this command line at the default workload (profiles/r1_tc3_ncu_summary.txt, profiles/r1_simt_ncu_summary.txt); bytes
+TRAFFIC = {'tc3': 88.46e6 + 280.49e6, 'simt': 17.6e6 + 103.3e6}
 
 
 def make_workload(n_c, seed=1111):
@@ -306,7 +309,7 @@ def main():
             'clocks': clocks,
             'gpu_launches': launches,
             'e2e': e2e,
-            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': TRAFFIC.get(args.engine) if args.points == 50000 else None,
                          'kernel': ('resid_simt_kernel<5>' if args.engine == 'simt' else 'resid_tc_kernel (tcgen05)') + ' (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
                          'flop_per_point': FLOP_PER_POINT,
                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in pk else 'fallback',
