@@ -401,3 +401,31 @@ def test_refeed_path_equals_resident_path(pe, golden, engine):
     b = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine).train(7, 5e-4, refeed=True)
     for x, y in zip(a, b):
         assert x == y
+
+
+# ------------------------------------------------------------------------------ BASELINE full sizes
+@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+def test_full_size_50k_parity_and_shard_additivity(pe, engine):
+    """BASELINE config 2 size (50,000 collocation + 5,000 hole points, 5x50 net): CUDA vs the float64 oracle on the full set,
+    and the size-independent property the multi-GPU path relies on: per-shard sums / N_global add up to the whole-set result."""
+    torch.set_num_threads(8)
+    import bench
+    Collo, HOLE = bench.make_workload(50000)
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    orc = R.Oracle('plate', Ws, bs)
+    T, loss, gref = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
+    m = _plate(pe, Collo, HOLE, layers, Ws, bs, engine=engine)
+    t, g = _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 1e-5, 2e-5)
+    # two "ranks" by hand: shard rows like engine.shard_range, keep the global denominators
+    from pinn_elastodynamics_b200.engine import shard_range
+    acc_t, acc_g = np.zeros(3), np.zeros_like(g, dtype=np.float64)
+    for r in range(2):
+        a, b = shard_range(50000, r, 2); ah, bh = shard_range(5000, r, 2)
+        ms = _plate(pe, Collo[a:b], HOLE[ah:bh], layers, Ws, bs, engine=engine)
+        for tm, n in zip(ms.engine.terms, (50000, 5000)):
+            tm.desc.n_global = n
+        ms.engine.evaluate()
+        acc_t += ms.engine.terms_host()[:3]; acc_g += ms.engine.grad_compact_host()
+    np.testing.assert_allclose(acc_t, t[:3], rtol=2e-6)
+    assert rel_err(acc_g, g) <= 5e-6
