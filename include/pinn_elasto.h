@@ -84,6 +84,9 @@ typedef struct pe_term_desc {
 int pe_version(void);
 const char *pe_last_error(void);
 
+/* sizeof(pe_term_desc) as compiled into the library: a binding (ctypes, cgo, ...) must assert that its mirror matches */
+int pe_abi_sizeof_term_desc(void);
+
 /* ---------------------------------------------------------------- plan (host only) */
 /* dims = [3, w1, ..., wL-1, O] as the reference's `uv_layers` (plate:885); device = CUDA ordinal or -1 for
    "no device" (layout queries only; lets the CPU test-suite exercise the host logic).  NULL on error. */
@@ -166,6 +169,11 @@ int pe_forward_fields(const pe_plan *plan, int formulation, const float *d_point
 int pe_forward_jets(const pe_plan *plan, int K, const float *d_points, int ld, int n,
                     const float *in_scale, const float *in_shift,
                     const float *d_params, float *d_out, void *stream);
+
+/* ---------------------------------------------------------------- debug / profiling */
+/* Per-phase cycle counters of the tensor-core residual kernel: d_counters16 = 16 device uint64 (or NULL to switch off);
+ * CTA 0 / thread 0 accumulates clock64 deltas per phase (tests/tc_phase_profile.py, profiles/r1_tc3_phase_cycles.txt). */
+void pe_debug_set_tc_profile(unsigned long long *d_counters16);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 SYMBOLS = [
     ('pe_version', _i, []),
     ('pe_last_error', C.c_char_p, []),
+    ('pe_abi_sizeof_term_desc', _i, []),
     ('pe_plan_create', _vp, [C.POINTER(_i), _i, _i]),
     ('pe_plan_destroy', None, [_vp]),
     ('pe_plan_param_count', _i, [_vp]),
@@ -61,6 +62,7 @@ SYMBOLS = [
     ('pe_reduce_adam', _i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     ('pe_forward_fields', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp, _vp, _vp]),
     ('pe_forward_jets', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp]),
+    ('pe_debug_set_tc_profile', None, [_vp]),
 ]
 
 _lib = None
@@ -90,6 +92,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.pe_abi_sizeof_term_desc() != C.sizeof(TermDesc):
+        raise ImportError(f'pe_term_desc ABI mismatch: library {lib.pe_abi_sizeof_term_desc()} bytes, ctypes mirror {C.sizeof(TermDesc)} bytes')
     _lib = lib
     return lib
 

@@ -23,6 +23,7 @@ size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
 size_t pe_tc_image_floats(const pe_plan* plan);
 
 extern "C" int pe_version(void) { return 100; }
+extern "C" int pe_abi_sizeof_term_desc(void) { return (int)sizeof(pe_term_desc); }
 extern "C" const char* pe_last_error(void) { return g_err; }
 
 static int build_layout(PeLayout& lay, const int* dims, int n_dims) {

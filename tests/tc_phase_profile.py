@@ -6,7 +6,7 @@ from oracle import ref_torch as R
 import pinn_elastodynamics_b200 as pe
 from pinn_elastodynamics_b200 import _lib as L
 lib = L.load()
-lib.pe_debug_set_tc_profile.argtypes = [C.c_void_p]
+
 layers = [3] + 5 * [50] + [5]
 rng = np.random.default_rng(0)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 50000

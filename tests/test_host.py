@@ -30,6 +30,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.pe_version() >= 100
 
 
+def test_term_desc_abi_matches_ctypes_mirror():
+    L, lib = _lib()
+    assert lib.pe_abi_sizeof_term_desc() == C.sizeof(L.TermDesc)
+
+
+def test_reference_chunk_arithmetic_of_the_wave_classes():
+    """batch_num chunk i = rows [int(i*N/B), int((i+1)*N/B)) (semi:299-302) -- the host logic of train(iter, lr, batch_num)"""
+    from pinn_elastodynamics_b200.models import _Base
+
+    class T:
+        global_n = 150397
+    o = _Base.__new__(_Base)
+    o._collo_term = T()
+    for B in (1, 3, 7):
+        ch = o._chunks(B)
+        assert ch[0][0] == 0 and ch[-1][1] == 150397 and all(ch[i][1] == ch[i + 1][0] for i in range(B - 1))
+        assert ch == [(int(i * 150397 / B), int((i + 1) * 150397 / B)) for i in range(B)]
+
+
 def test_layout_pack_unpack_roundtrip():
     L, lib = _lib()
     for layers in ([3, 50, 50, 50, 50, 50, 5], [3] + 8 * [70] + [5], [3] + 8 * [100] + [7], [3] + 6 * [140] + [7], [3, 20, 20, 20, 20, 5], [3, 7, 5]):
