@@ -191,7 +191,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--steps', type=int, default=1500)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--engine', default='tc3', help='tc3 = tcgen05 engine (fp32-parity split), simt = fp32 FFMA engine, tc1 = single-pass TF32')

@@ -48,7 +48,7 @@ constexpr int TC_STASH_LAYER = 5 * TC_STASH_STREAM;
 
 constexpr int SM_ACT = 0;
 constexpr int SM_WIMG = SM_ACT + 5 * TC_ACT_STREAM;          // 144,480
-constexpr int SM_STAGE = SM_WIMG + TC_IMG_SET;               // 181,344
+constexpr int SM_STAGE = SM_WIMG + TC_IMG_SET;               // 181,344: bf16 hi/mid images of Zbar for the weight-gradient MMAs
 constexpr int SM_MISC = SM_STAGE + TC_ACT_STREAM;            // 210,240
 constexpr int SM_COORD = SM_MISC + 64;                       // 128 x 4 floats
 constexpr int SM_RED = SM_COORD + 128 * 16;                  // 4 x 64 x 4 floats scratch (layer-1 gradient) / term sums
@@ -224,7 +224,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     const int fast = args.fast;
     uint8_t* act = smem + SM_ACT;
     uint8_t* wimg = smem + SM_WIMG;
-    uint8_t* stage = smem + SM_STAGE;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SM_MISC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC + 16);
     float* coord = reinterpret_cast<float*>(smem + SM_COORD);       // [128][4]: a0x, a0y, a0t, valid
