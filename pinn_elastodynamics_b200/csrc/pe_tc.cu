@@ -70,6 +70,13 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d, uint64_t a, uint64_t b, 
 __device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t id, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(id), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t id, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+// smem -> TMEM copy of one K-step of an activation operand (128 rows x 32 B -> 8 columns); ordered with the MMAs of the issuing thread
+__device__ __forceinline__ void tm_cp_128x256b(uint32_t taddr, uint64_t sd) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sd) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -156,7 +163,12 @@ struct TcArgs {
 #define TC_PROF(slot) do { if (args.prof && blockIdx.x == 0 && tid == 0) { long long now_ = clock64(); prof_acc[slot] += (unsigned long long)(now_ - prof_t); prof_t = now_; } } while (0)
 
 // ---- issue the MMAs of one layer GEMM for all 5 streams (one thread).  ksteps = K/8 (tf32), kb = K/16 (bf16).
-// Descriptors are built once; a K-step only adds a constant to the 14-bit start-address field (no carry: smem < 256 KB).
+// SS-mode TF32 MMAs with K = 8 and N = 64 are shared-memory-operand bound (each re-reads its 4 KB A tile at ~64 B/clk:
+// ~105 cycles per MMA measured against a 32-cycle issue floor), and the fp32 operand is used twice (Whi, Wlo).  So the
+// activation stream is copied ONCE into tensor memory (tcgen05.cp, in order with the MMAs) and the products run in TS
+// mode (A from TMEM, only the 2 KB weight tile comes from smem).  TMEM has no spare columns, but while stream k < 4 is
+// multiplied the accumulator columns of stream 4 are still unused, and for stream 4 the lo-operand columns of streams
+// 0/1 are already dead -- those serve as the 56-column operand window.
 __device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint32_t wimg_s, int N, int ksteps, int kb, int fast) {
     const uint32_t id32 = idesc_tf32(N), id16 = idesc_bf16(N);
     const uint32_t nrow = (uint32_t)N * 16u;
@@ -165,14 +177,18 @@ __device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
         const uint32_t d = tbase + TM_ACC + 64u * k;
+        const uint32_t win = tbase + ((k < 4) ? (TM_ACC + 256u) : TM_LO);
         const uint64_t a0 = sdesc(act_s + (uint32_t)k * TC_ACT_STREAM, TC_CH, 128);
 #pragma unroll
         for (int s = 0; s < 7; ++s)
-            if (s < ksteps) mma_tf32_ss(d, a0 + s * a_step, b_hi + s * b_step, id32, s > 0);
+            if (s < ksteps) tm_cp_128x256b(win + 8u * s, a0 + s * a_step);
+#pragma unroll
+        for (int s = 0; s < 7; ++s)
+            if (s < ksteps) mma_tf32_ts(d, win + 8u * s, b_hi + s * b_step, id32, s > 0);
         if (!fast) {
 #pragma unroll
             for (int s = 0; s < 7; ++s)
-                if (s < ksteps) mma_tf32_ss(d, a0 + s * a_step, b_lo + s * b_step, id32, 1);
+                if (s < ksteps) mma_tf32_ts(d, win + 8u * s, b_lo + s * b_step, id32, 1);
 #pragma unroll
             for (int s = 0; s < 4; ++s)
                 if (s < kb) mma_bf16_ts(d, tbase + TM_LO + 32u * k + 8u * s, b_bf + s * b_step, id16, 1);
@@ -380,6 +396,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                         tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(z[k][0], z[k][1]), lo_pair(z[k][2], z[k][3]));
                     }
                 }
+                if (h == 1) {      // units 56..63 of the lo operands: stream 0's were used as the TS operand window, keep them finite/zero
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
+                }
             } else if (h == 0) {
                 // ---------------- outputs -> residuals -> loss partials -> seeds (adjoint of the outputs)
                 float Y[5][PE_UJ];
@@ -418,6 +438,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + 1 * TC_CH + p * 16) = v1;
                     tm_st2(tlane + TM_LO + 32 * k + 0, lo_pair(v0.x, v0.y), lo_pair(v0.z, v0.w));
                     tm_st2(tlane + TM_LO + 32 * k + 2, lo_pair(v1.x, 0.f), 0u);
+                    tm_st2(tlane + TM_LO + 32 * k + 4, 0u, 0u);        // units 8..15: read by the K = 16 bf16 step of the adjoint MMA,
+                    tm_st2(tlane + TM_LO + 32 * k + 6, 0u, 0u);        // may hold the TS operand window of the forward pass
                 }
             }
         }
@@ -588,6 +610,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     *reinterpret_cast<float4*>(act + k * TC_ACT_STREAM + c * TC_CH + p * 16) = v;
                     tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(v.x, v.y), lo_pair(v.z, v.w));
                 }
+            }
+            if (h == 1) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
             }
         }
         TC_PROF(13);

@@ -122,6 +122,31 @@ def t_mnmajor_bf16(M=64, N=56, P=128, swap=False, three=False):
     return np.array_equal(got, exp), got, exp
 
 
+def t_cp_and_tf32_ts(K=56, N=64, shape=4):
+    """tcgen05.cp smem -> TMEM of the activation operand ([chunk][point][4 fp32] layout), dumped, then used as the A operand of
+    kind::tf32 TS MMAs (A from tensor memory) against a K-major B in smem; the MMA reads the window after the copy (in-order pipe)."""
+    rng = np.random.default_rng(8)
+    A = rng.integers(-3, 4, (128, K)).astype(np.float32)
+    B = rng.integers(-3, 4, (N, K)).astype(np.float32)
+    ia, ib = chunked(A, 4), chunked(B, 4)
+    smem = np.concatenate([ia.ravel(), ib.ravel()])
+    offb = ia.size * 4
+    win = 256                                  # TMEM column of the A window
+    ops = []
+    if shape == 4:                             # 128x256b: one K-step (2 chunks, LBO = 2048) per copy
+        for s in range(K // 8):
+            ops.append((4, sdesc(s * 2 * 2048, 2048, 128), 0, 0, win + 8 * s, 0))
+    else:                                      # 128x128b: one chunk per copy
+        for c in range(K // 4):
+            ops.append((5, sdesc(c * 2048, 2048, 128), 0, 0, win + 4 * c, 0))
+    for s in range(K // 8):
+        ops.append((3, win + 8 * s, sdesc(offb + s * 2 * N * 16, N * 16, 128), idesc(2, 128, N), 0, 1 if s else 0))
+    out = run(smem, ops, 512)
+    ok_copy = np.array_equal(out[:, win:win + K], A)
+    ok_mma = np.array_equal(out[:, :N], A @ B.T)
+    return ok_copy and ok_mma, ok_copy, ok_mma, out[:, win:win + K], A
+
+
 def t_bf16_ss(K=16, N=64):
     rng = np.random.default_rng(3)
     A = rng.integers(-3, 4, (128, K)).astype(np.float32)
@@ -181,6 +206,7 @@ TESTS = [('kmajor tf32 K=8', lambda: t_kmajor_tf32()), ('kmajor tf32 K=8 swapped
          ('bf16 TS K=16', lambda: t_bf16_ts()), ('bf16 TS K=64', lambda: t_bf16_ts(K=64)), ('mixed tf32 SS + bf16 TS accumulate', lambda: t_bf16_ts(K=64, mixed=True)),
          ('mnmajor bf16 M=64 N=56', lambda: t_mnmajor_bf16()), ('mnmajor bf16 swapped', lambda: t_mnmajor_bf16(swap=True)),
          ('mnmajor bf16 M=128 N=64', lambda: t_mnmajor_bf16(M=128, N=64)),
+         ('cp 128x256b + tf32 TS', lambda: t_cp_and_tf32_ts(shape=4)), ('cp 128x128b + tf32 TS', lambda: t_cp_and_tf32_ts(shape=5)),
          ('tf32 conversion', None)]
 
 
