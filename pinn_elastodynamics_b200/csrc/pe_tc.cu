@@ -163,36 +163,37 @@ struct TcArgs {
 #define TC_PROF(slot) do { if (args.prof && blockIdx.x == 0 && tid == 0) { long long now_ = clock64(); prof_acc[slot] += (unsigned long long)(now_ - prof_t); prof_t = now_; } } while (0)
 
 // ---- issue the MMAs of one layer GEMM for all 5 streams (one thread).  ksteps = K/8 (tf32), kb = K/16 (bf16).
-// SS-mode TF32 MMAs with K = 8 and N = 64 are shared-memory-operand bound (each re-reads its 4 KB A tile at ~64 B/clk:
-// ~105 cycles per MMA measured against a 32-cycle issue floor), and the fp32 operand is used twice (Whi, Wlo).  So the
-// activation stream is copied ONCE into tensor memory (tcgen05.cp, in order with the MMAs) and the products run in TS
-// mode (A from TMEM, only the 2 KB weight tile comes from smem).  TMEM has no spare columns, but while stream k < 4 is
-// multiplied the accumulator columns of stream 4 are still unused, and for stream 4 the lo-operand columns of streams
-// 0/1 are already dead -- those serve as the 56-column operand window.
+// Back-to-back MMAs that accumulate into the SAME TMEM tile form a dependent chain and run at pipeline LATENCY (~100 cycles
+// per 128x64x8 MMA measured, against a 32-cycle throughput floor; moving the A operand to tensor memory did not change that).
+// The 5 jet streams have 5 independent accumulators, so the K-steps are issued stream-interleaved: consecutive MMAs never
+// touch the same accumulator.
 __device__ __forceinline__ void issue_layer(uint32_t tbase, uint32_t act_s, uint32_t wimg_s, int N, int ksteps, int kb, int fast) {
     const uint32_t id32 = idesc_tf32(N), id16 = idesc_bf16(N);
     const uint32_t nrow = (uint32_t)N * 16u;
     const uint64_t a_step = (uint64_t)((2u * TC_CH) >> 4), b_step = (uint64_t)((2u * nrow) >> 4);
     const uint64_t b_hi = sdesc(wimg_s + TC_IMG_HI, nrow, 128), b_lo = sdesc(wimg_s + TC_IMG_LO, nrow, 128), b_bf = sdesc(wimg_s + TC_IMG_BF, nrow, 128);
-#pragma unroll 1
-    for (int k = 0; k < 5; ++k) {
-        const uint32_t d = tbase + TM_ACC + 64u * k;
-        const uint32_t win = tbase + ((k < 4) ? (TM_ACC + 256u) : TM_LO);
-        const uint64_t a0 = sdesc(act_s + (uint32_t)k * TC_ACT_STREAM, TC_CH, 128);
+    const uint64_t a0 = sdesc(act_s, TC_CH, 128);
+    const uint64_t a_stream = (uint64_t)(TC_ACT_STREAM >> 4);
+    const uint32_t d0 = tbase + TM_ACC;
 #pragma unroll
-        for (int s = 0; s < 7; ++s)
-            if (s < ksteps) tm_cp_128x256b(win + 8u * s, a0 + s * a_step);
+    for (int s = 0; s < 7; ++s)
+        if (s < ksteps) {
 #pragma unroll
-        for (int s = 0; s < 7; ++s)
-            if (s < ksteps) mma_tf32_ts(d, win + 8u * s, b_hi + s * b_step, id32, s > 0);
-        if (!fast) {
-#pragma unroll
-            for (int s = 0; s < 7; ++s)
-                if (s < ksteps) mma_tf32_ts(d, win + 8u * s, b_lo + s * b_step, id32, 1);
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (s < kb) mma_bf16_ts(d, tbase + TM_LO + 32u * k + 8u * s, b_bf + s * b_step, id16, 1);
+            for (int k = 0; k < 5; ++k) mma_tf32_ss(d0 + 64u * k, a0 + k * a_stream + s * a_step, b_hi + s * b_step, id32, s > 0);
         }
+    if (!fast) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s)
+            if (s < ksteps) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) mma_tf32_ss(d0 + 64u * k, a0 + k * a_stream + s * a_step, b_lo + s * b_step, id32, 1);
+            }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (s < kb) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) mma_bf16_ts(d0 + 64u * k, tbase + TM_LO + 32u * k + 8u * s, b_bf + s * b_step, id16, 1);
+            }
     }
 }
 
@@ -534,9 +535,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
 #pragma unroll
                     for (int s8 = 0; s8 < 8; ++s8) {     // 16 points per MMA: start address += 256 B
                         const uint64_t o = (uint64_t)(s8 * 16);
-                        mma_bf16_ss(d, ahi + o, zhi + o, id, (k > 0 || s8 > 0) ? 1u : 0u);
-                        mma_bf16_ss(d, ahi + o, zmid + o, id, 1u);
-                        mma_bf16_ss(d, amid + o, zhi + o, id, 1u);
+                        // two accumulator tiles (even / odd K-steps, 64 columns apart): consecutive MMAs alternate between two
+                        // independent chains instead of serialising on one accumulator; the drain adds them
+                        const uint32_t dd = d + ((s8 & 1) ? 64u : 0u);
+                        const uint32_t first = (k == 0 && s8 < 2) ? 0u : 1u;
+                        mma_bf16_ss(dd, ahi + o, zhi + o, id, first);
+                        mma_bf16_ss(dd, ahi + o, zmid + o, id, 1u);
+                        mma_bf16_ss(dd, amid + o, zhi + o, id, 1u);
                     }
                     mma_commit(bar_s);
                 }
@@ -555,9 +560,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 float* gB = gpart + lay.boff[m];
                 const int c_lo = h ? 32 : 0, c_hi = h ? 56 : 32;
                 for (int c = c_lo; c < c_hi; c += 8) {
-                    float v[8];
+                    float v[8], v2[8];
                     tm_ld8(tlane + TM_LO + c, v);
+                    tm_ld8(tlane + TM_LO + 64 + c, v2);
                     tm_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += v2[q];
                     if (lane < 16 && c < NZ) {
                         float* dst = (i < din) ? gW + (size_t)i * ldw + c : ((i == 63) ? gB + c : nullptr);
                         if (dst) {
@@ -566,8 +574,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                         }
                     }
                 }
-                // the tile aliased the lo-operand columns of streams 0/1 including stream 0's zero pad (units 56..63): restore it
-                if (h == 0) { tm_st2(tlane + TM_LO + 28, 0u, 0u); tm_st2(tlane + TM_LO + 30, 0u, 0u); }
+                // the two tiles aliased the lo-operand columns of streams 0..3 (320..439) including zero pads (units 56..63): restore them
+                if (h == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
+                }
             }
             TC_PROF(12);
             // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
