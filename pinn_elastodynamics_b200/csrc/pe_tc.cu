@@ -528,20 +528,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 TC_PROF(9);
                 if (tid == 0) {
                     fence_after();
-                    const uint32_t id = idesc_bf16_mn(64, NZ);
+                    // hh and hm in ONE MMA: the Zhi and Zmid images are contiguous (7 + 7 chunks of 8 units), so a B operand with
+                    // N = 112 starting at Zhi yields D[:, 0:56] = Ahi^T Zhi and D[:, 56:112] = Ahi^T Zmid; mh goes into D[:, 0:56].
+                    const uint32_t id2 = idesc_bf16_mn(64, 56 + NZ), id1 = idesc_bf16_mn(64, NZ);
                     const uint32_t d = tbase + TM_LO;
                     const uint64_t ahi = sdesc(smem_u32(smem + DW_AHI), 128, 2048), amid = sdesc(smem_u32(smem + DW_AMID), 128, 2048);
-                    const uint64_t zhi = sdesc(smem_u32(smem + DW_ZHI), 128, 2048), zmid = sdesc(smem_u32(smem + DW_ZMID), 128, 2048);
+                    const uint64_t zhi = sdesc(smem_u32(smem + DW_ZHI), 128, 2048);
 #pragma unroll
                     for (int s8 = 0; s8 < 8; ++s8) {     // 16 points per MMA: start address += 256 B
                         const uint64_t o = (uint64_t)(s8 * 16);
-                        // two accumulator tiles (even / odd K-steps, 64 columns apart): consecutive MMAs alternate between two
-                        // independent chains instead of serialising on one accumulator; the drain adds them
-                        const uint32_t dd = d + ((s8 & 1) ? 64u : 0u);
-                        const uint32_t first = (k == 0 && s8 < 2) ? 0u : 1u;
-                        mma_bf16_ss(dd, ahi + o, zhi + o, id, first);
-                        mma_bf16_ss(dd, ahi + o, zmid + o, id, 1u);
-                        mma_bf16_ss(dd, amid + o, zhi + o, id, 1u);
+                        mma_bf16_ss(d, ahi + o, zhi + o, id2, (k > 0 || s8 > 0) ? 1u : 0u);
+                        mma_bf16_ss(d, amid + o, zhi + o, id1, 1u);
                     }
                     mma_commit(bar_s);
                 }
@@ -562,7 +559,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 for (int c = c_lo; c < c_hi; c += 8) {
                     float v[8], v2[8];
                     tm_ld8(tlane + TM_LO + c, v);
-                    tm_ld8(tlane + TM_LO + 64 + c, v2);
+                    tm_ld8(tlane + TM_LO + 56 + c, v2);          // the hm block
                     tm_wait_ld();
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] += v2[q];
