@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                         const float w0 = __ldg(W0 + j), w1 = __ldg(W0 + ldw + j), w2 = __ldg(W0 + 2 * ldw + j);
                         z[0] = fmaf(c4.x, w0, fmaf(c4.y, w1, c4.z * w2));
                         z[1] = Tc.in_scale[0] * w0; z[2] = Tc.in_scale[1] * w1; z[3] = Tc.in_scale[2] * w2; z[4] = 0.f;
-                        act_fwd<5>(z, __ldg(b0 + j));
+                        act_fwd<5, true>(z, __ldg(b0 + j));
                     }
 #pragma unroll
                     for (int k = 0; k < 5; ++k) o[k][u] = z[k];
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                         float zz[5];
 #pragma unroll
                         for (int k = 0; k < 5; ++k) zz[k] = z[k][u];
-                        if (j < dout) act_fwd<5>(zz, __ldg(bias + j));
+                        if (j < dout) act_fwd<5, true>(zz, __ldg(bias + j));
                         else {
 #pragma unroll
                             for (int k = 0; k < 5; ++k) zz[k] = 0.f;
