@@ -52,7 +52,9 @@ constexpr int SM_STAGE = SM_WIMG + TC_IMG_SET;               // 181,344: bf16 hi
 constexpr int SM_MISC = SM_STAGE + TC_ACT_STREAM;            // 210,240
 constexpr int SM_COORD = SM_MISC + 64;                       // 128 x 4 floats
 constexpr int SM_RED = SM_COORD + 128 * 16;                  // 4 x 64 x 4 floats scratch (layer-1 gradient) / term sums
-constexpr int SM_TOTAL = SM_RED + 4096;
+constexpr int SM_BIAS = SM_RED + 4096;                        // 64 floats: bias of the current layer
+constexpr int SM_W0 = SM_BIAS + 256;                          // [4][64] floats: first-layer weight rows 0..2 and bias
+constexpr int SM_TOTAL = SM_W0 + 1024;
 
 constexpr uint32_t TM_ACC = 0, TM_LO = 320;
 
@@ -245,6 +247,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC + 16);
     float* coord = reinterpret_cast<float*>(smem + SM_COORD);       // [128][4]: a0x, a0y, a0t, valid
     float* red = reinterpret_cast<float*>(smem + SM_RED);
+    float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);   // biases come from smem: with 217 KB of smem there is no L1 left and a
+    float* sw0 = reinterpret_cast<float*>(smem + SM_W0);       // global bias load in the tanh dependency chain costs an L2 round trip
     const uint32_t act_s = smem_u32(act), wimg_s = smem_u32(wimg), bar_s = smem_u32(mbar);
 
     for (int i = tid; i < SM_TOTAL / 16; i += TC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -254,6 +258,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     const float* __restrict__ params = A.params;
     for (int i = tid; i < lay.total; i += TC_THREADS) __stcg(gpart + i, 0.f);
     __syncthreads();
+    if (tid < 64) {                                  // first-layer weights (3 x d1) and bias -> smem, once per launch
+        const bool in = tid < lay.d[1];
+        sw0[tid] = in ? __ldg(params + lay.woff[0] + tid) : 0.f;
+        sw0[64 + tid] = in ? __ldg(params + lay.woff[0] + lay.ldw[0] + tid) : 0.f;
+        sw0[128 + tid] = in ? __ldg(params + lay.woff[0] + 2 * lay.ldw[0] + tid) : 0.f;
+        sw0[192 + tid] = in ? __ldg(params + lay.boff[0] + tid) : 0.f;
+    }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -282,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
     __syncthreads();
     fence_after();
 
+    float bias_pre = (tid < 64 && tid < lay.d[2]) ? __ldg(params + lay.boff[1] + tid) : 0.f;   // bias of the next TC layer, prefetched like the images
     float4 img[9];                                   // one operand-image set (36,864 B / 256 threads), prefetched a phase ahead
 #pragma unroll
     for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(args.images + (size_t)1 * TC_IMG_LAYER) + tid + i * TC_THREADS);
@@ -308,9 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
         // ================================================================ layer 1 (3 -> d1): per-thread FFMA
         {
             const float4 c4 = *reinterpret_cast<const float4*>(coord + 4 * p);
-            const float* W0 = params + lay.woff[0];
-            const float* b0 = params + lay.boff[0];
-            const int ldw = lay.ldw[0], dout = lay.d[1];
+            const int dout = lay.d[1];
             float* st = stash;                                         // stash layer index 0 = outputs of layer 1
 #pragma unroll 1
             for (int c = 7 * h; c < 7 * h + 7; ++c) {
@@ -320,10 +330,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     const int j = 4 * c + u;
                     float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                     if (j < dout) {
-                        const float w0 = __ldg(W0 + j), w1 = __ldg(W0 + ldw + j), w2 = __ldg(W0 + 2 * ldw + j);
+                        const float w0 = sw0[j], w1 = sw0[64 + j], w2 = sw0[128 + j];
                         z[0] = fmaf(c4.x, w0, fmaf(c4.y, w1, c4.z * w2));
                         z[1] = Tc.in_scale[0] * w0; z[2] = Tc.in_scale[1] * w1; z[3] = Tc.in_scale[2] * w2; z[4] = 0.f;
-                        act_fwd<5, true>(z, __ldg(b0 + j));
+                        act_fwd<5, true>(z, sw0[192 + j]);
                     }
 #pragma unroll
                     for (int k = 0; k < 5; ++k) o[k][u] = z[k];
@@ -343,9 +353,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
             const int m = l - 1;                                       // weight matrix index
             const int dout = lay.d[l];
             const int NF = (dout <= 16) ? 16 : 64;
-            // operand images of matrix m (prefetched into registers one phase ahead) -> smem
+            // operand images of matrix m (prefetched into registers one phase ahead) -> smem, and the layer's bias
 #pragma unroll
             for (int i = 0; i < 9; ++i) reinterpret_cast<float4*>(wimg)[tid + i * TC_THREADS] = img[i];
+            if (tid < 64) sbias[tid] = bias_pre;
             tm_wait_st();
             fence_async_smem();
             fence_before();
@@ -361,13 +372,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 const uint8_t* nsrc = (l < L) ? args.images + (size_t)(m + 1) * TC_IMG_LAYER : args.images + (size_t)m * TC_IMG_LAYER + TC_IMG_SET;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(nsrc) + tid + i * TC_THREADS);
+                if (l < L) bias_pre = (tid < 64 && tid < lay.d[l + 1]) ? __ldg(params + lay.boff[l] + tid) : 0.f;
             }
             mbar_wait(bar_s, parity);
             parity ^= 1;
             fence_after();
             TC_PROF(3);
             if (l < L) {
-                const float* bias = params + lay.boff[m];
                 float* st = stash + (size_t)(l - 1) * (TC_STASH_LAYER / 4);
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                         float zz[5];
 #pragma unroll
                         for (int k = 0; k < 5; ++k) zz[k] = z[k][u];
-                        if (j < dout) act_fwd<5, true>(zz, __ldg(bias + j));
+                        if (j < dout) act_fwd<5, true>(zz, sbias[j]);
                         else {
 #pragma unroll
                             for (int k = 0; k < 5; ++k) zz[k] = 0.f;
@@ -401,10 +412,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
 #pragma unroll
                     for (int k = 0; k < 5; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
                 }
+                TC_PROF(5);
             } else if (h == 0) {
                 // ---------------- outputs -> residuals -> loss partials -> seeds (adjoint of the outputs)
                 float Y[5][PE_UJ];
-                const float* bias = params + lay.boff[m];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     float v[8];
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     for (int u = 0; u < PE_UJ; ++u) Y[k][u] = (u < 8 && u < dout) ? v[u < 8 ? u : 0] : 0.f;
                 }
 #pragma unroll
-                for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += __ldg(bias + u);
+                for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += sbias[u];
                 if (!sec) {
                     const float* aux_row = A.aux ? A.aux + (size_t)(valid ? pt : 0) * 50 : nullptr;
                     residual_stage<5>(Y, T, aux_row, row, valid, A.inv_n, tsum);
@@ -466,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 const uint8_t* nsrc = (l > 2) ? args.images + (size_t)(m - 1) * TC_IMG_LAYER + TC_IMG_SET : args.images + (size_t)1 * TC_IMG_LAYER;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) img[i] = __ldg(reinterpret_cast<const float4*>(nsrc) + tid + i * TC_THREADS);
+                if (l == 2) bias_pre = (tid < 64 && tid < lay.d[2]) ? __ldg(params + lay.boff[1] + tid) : 0.f;   // next tile's first TC layer
             }
             // ---- weight / bias gradient of layer l on the tensor cores (bf16 hi/mid operands, see above)
             const float* stash_in = stash + (size_t)(l - 2) * (TC_STASH_LAYER / 4);      // outputs of layer l-1 = inputs A of layer l

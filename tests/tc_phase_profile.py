@@ -21,7 +21,7 @@ for _ in range(steps): m.engine.adam_step(5e-4)
 torch.cuda.synchronize()
 lib.pe_debug_set_tc_profile(None)
 p = prof.cpu().numpy().astype(np.float64) / steps
-names = ['layer1 fwd', 'fwd img+sync', 'fwd mma issue', 'fwd mma wait', 'fwd epilogue(+resid)', '-', 'bwd img+sync', 'adj issue', 'convZ0+loadA0+adj wait',
+names = ['layer1 fwd', 'fwd img+sync', 'fwd mma issue', 'fwd mma wait', 'fwd resid stage', 'fwd epilogue (thread 0)', 'bwd img+sync', 'adj issue', 'convZ0+loadA0+adj wait',
          'dW convert+sync', 'dW issue', 'dW wait', 'dW drain', 'bwd epilogue', 'layer1 grad', 'tile start']
 tiles = (N + 127) // 128 / 148
 print('cycles per step (CTA 0), tiles per CTA ~%.2f' % tiles)
