@@ -525,6 +525,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                 }
             };
             load_A(0);
+            if (l >= 3) {   // pull the stash layer of the next (shallower) iteration towards L2 while this layer's MMAs run
+                const char* nxt = reinterpret_cast<const char*>(stash + (size_t)(l - 3) * (TC_STASH_LAYER / 4));
+                for (int i = tid; i < TC_STASH_LAYER / 128; i += TC_THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)i * 128));
+            }
             conv_Z(0);                                   // STAGE region: free while the adjoint MMAs read WIMG / ACT / LO
             mbar_wait(bar_s, parity);                    // adjoint MMAs done: WIMG region and the LO columns are free now
             parity ^= 1;
@@ -533,6 +538,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
 #pragma unroll 1
             for (int k = 0; k < 5; ++k) {
                 store_A(k);
+                if (k < 4) load_A(k + 1);                // next stream's stash loads: issued as early as the registers are free
                 if (k > 0) conv_Z(k);
                 fence_async_smem();
                 fence_before();
@@ -555,7 +561,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) resid_tc_kernel(const TcArgs ar
                     mma_commit(bar_s);
                 }
                 TC_PROF(10);
-                if (k < 4) load_A(k + 1);                // in flight while the MMAs of stream k run
                 mbar_wait(bar_s, parity);
                 parity ^= 1;
                 TC_PROF(11);
