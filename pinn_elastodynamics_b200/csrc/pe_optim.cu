@@ -6,7 +6,7 @@
 namespace {
 
 #define RED_TX 32      // float4 columns per block
-#define RED_TY 8       // slot groups per block
+#define RED_TY 16      // slot groups per block
 
 // blockDim = (RED_TX, RED_TY).  Thread (tx, ty) sums slots ty, ty+RED_TY, ... of float4 column i4 (4 loads in
 // flight), the RED_TY partials are then added in fixed order by ty == 0: deterministic for a given n_slots.

@@ -121,7 +121,7 @@ __device__ __forceinline__ uint32_t lo_pair(float x0, float x1) {
 // matrix: forward B operand [n = out unit j][k = in unit i] and adjoint B operand [n = i][k = j], each as tf32-hi,
 // tf32-lo (4-float chunks) and bf16 (8-element chunks).  Zero padded to K = 56 (64 for bf16), N = 64.
 __global__ void tc_prep_kernel(const float* __restrict__ params, PeLayout lay, uint8_t* __restrict__ images) {
-    const int m = blockIdx.x;                       // matrix index 0..L-1
+    const int m = blockIdx.x >> 4;                  // matrix index 0..L-1; 16 blocks of 256 elements per matrix (latency-bound otherwise)
     const int din = lay.d[m], dout = lay.d[m + 1], ldw = lay.ldw[m];
     const float* W = params + lay.woff[m];
     uint8_t* img = images + (size_t)m * TC_IMG_LAYER;
@@ -132,7 +132,8 @@ __global__ void tc_prep_kernel(const float* __restrict__ params, PeLayout lay, u
     float* alo = reinterpret_cast<float*>(img + TC_IMG_SET + TC_IMG_LO);
     __nv_bfloat16* abf = reinterpret_cast<__nv_bfloat16*>(img + TC_IMG_SET + TC_IMG_BF);
     const int NF = (dout <= 16) ? 16 : 64;          // forward N
-    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    {
+        const int e = (blockIdx.x & 15) * 256 + threadIdx.x;
         const int i = e >> 6, j = e & 63;
         const float w = (i < din && j < dout) ? W[(size_t)i * ldw + j] : 0.f;
         const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
@@ -758,7 +759,7 @@ int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int eng
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
     uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
     t.images = images;
-    tc_prep_kernel<<<plan->lay.L, 256, 0, st>>>(a.params, a.lay, images);
+    tc_prep_kernel<<<plan->lay.L * 16, 256, 0, st>>>(a.params, a.lay, images);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("tc_prep_kernel: %s", cudaGetErrorString(e)); return 3; }
     e = cudaFuncSetAttribute(resid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024);
