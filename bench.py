@@ -36,7 +36,7 @@ FLOP_PER_POINT = 6 * 5 * S_WEIGHTS                                            # 
 METRIC = 'collocation-pt residual+grad evals/sec per Adam step'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures of
 # this command line at the default workload (profiles/r1_tc3_ncu_summary.txt, profiles/r1_simt_ncu_summary.txt); bytes
-TRAFFIC = {'tc3': 87.31e6 + 280.74e6, 'simt': 17.6e6 + 103.3e6}
+TRAFFIC = {'tc3': 112.27e6 + 282.54e6, 'simt': 17.6e6 + 103.3e6}
 
 
 def make_workload(n_c, seed=1111):
