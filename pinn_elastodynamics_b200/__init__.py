@@ -8,7 +8,7 @@ Importing this package does not touch the GPU; constructing a model requires one
 from . import _lib
 from ._lib import PeError
 
-__all__ = ['PINN', 'PhysicsInformedNN', 'DeepHPM', 'DeepElasticWave', 'Network', 'LossEngine', 'PeError']
+__all__ = ['PINN', 'PhysicsInformedNN', 'DeepHPM', 'DeepElasticWave', 'Network', 'LossEngine', 'PeError', 'preprocess']
 
 
 def __getattr__(name):
@@ -18,4 +18,7 @@ def __getattr__(name):
     if name in ('Network', 'LossEngine'):
         from . import engine
         return getattr(engine, name)
+    if name == 'preprocess':
+        import importlib
+        return importlib.import_module('.preprocess', __name__)
     raise AttributeError(name)

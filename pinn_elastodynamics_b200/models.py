@@ -222,6 +222,15 @@ class _Base:
     def probe(self, x_star, y_star, t_star):
         return self.predict(x_star, y_star, t_star)
 
+    def predict_frames(self, x_star, y_star, times):
+        """All output frames in ONE launch (the reference drivers call predict() once per frame, 8 sess.run each:
+        plate:980-998, semi:907-922).  Returns a list with one predict()-style 8-tuple per time in `times`."""
+        x = _col(x_star); y = _col(y_star)
+        n, times = x.shape[0], np.asarray(times, dtype=np.float64).ravel()
+        X = np.concatenate([np.tile(x, (len(times), 1)), np.tile(y, (len(times), 1)), np.repeat(times, n)[:, None]], 1)
+        out = self.predict(X[:, 0:1], X[:, 1:2], X[:, 2:3])
+        return [tuple(f[i * n:(i + 1) * n] for f in out) for i in range(len(times))]
+
 
 # ======================================================================================= plate
 class PINN(_Base):

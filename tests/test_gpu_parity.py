@@ -429,3 +429,34 @@ def test_full_size_50k_parity_and_shard_additivity(pe, engine):
         acc_t += ms.engine.terms_host()[:3]; acc_g += ms.engine.grad_compact_host()
     np.testing.assert_allclose(acc_t, t[:3], rtol=2e-6)
     assert rel_err(acc_g, g) <= 5e-6
+
+
+# ------------------------------------------------------------------------------ driver recipe end to end
+def test_plate_recipe_end_to_end(pe, golden):
+    """The reference driver's sequence on a shrunken problem: sample point sets -> PINN -> train_bfgs_dist -> train_bfgs_part ->
+    Adam -> L-BFGS -> save/load -> frame-batched predict -> FEM metrics (plate:892-998).  Checks that every stage runs, the loss
+    decreases, and that predict_frames (one launch) equals per-frame predict (the reference's loop)."""
+    from pinn_elastodynamics_b200 import preprocess as P
+    S = P.plate_point_sets(rng=np.random.default_rng(11), scale=0.01)
+    uv, dl, pl = [3, 30, 30, 30, 5], [3, 10, 10, 5], [3, 10, 10, 5]
+    m = pe.PINN(S['Collo'], S['HOLE'][::10], S['IC'], S['LF'], S['RT'], S['UP'], S['LW'], S['DIST'][::5], uv, dl, pl, S['lb'], S['ub'],
+                verbose=False, engine='tc3')
+    opts = dict(maxiter=40, maxfun=60, maxcor=50, maxls=50, ftol=1e-5 * np.finfo(float).eps)
+    m.train_bfgs_dist(opts); m.train_bfgs_part(opts)
+    v0 = m.getloss()
+    hist = m.train(30, 5e-4)
+    assert np.isfinite(hist[3]).all() and hist[3][-1] < v0['loss']
+    seq = []
+    m.callback = lambda l: seq.append(l)
+    m.train_bfgs(opts)
+    assert seq[-1] < hist[3][-1]
+    g = golden('plate_ckpt.npz')
+    A = g['fem20']
+    times = [1.25, 2.5, 6.25]
+    frames = m.predict_frames(A[:, 0:1], A[:, 1:2], times)
+    for t, fr in zip(times, frames):
+        one = m.predict(A[:, 0:1], A[:, 1:2], np.full((A.shape[0], 1), t))
+        for a, b in zip(fr, one):
+            np.testing.assert_array_equal(a, b)
+    met = P.fem_metrics(frames[1][:5], [A[:, 2 + i] for i in range(5)])
+    assert set(met) == {'u', 'v', 's11', 's22', 's12'} and all(np.isfinite(list(met.values())))

@@ -1,0 +1,69 @@
+"""CPU tests of the vectorised host preprocessing against loop restatements of the reference helpers."""
+import numpy as np
+
+from oracle import preprocess_loops as O
+from pinn_elastodynamics_b200 import preprocess as P
+
+
+def test_lhs_is_a_latin_hypercube_and_follows_the_global_stream():
+    np.random.seed(1111)
+    H = P.lhs(3, 1000)
+    assert H.shape == (1000, 3) and H.min() >= 0 and H.max() <= 1
+    for j in range(3):      # exactly one point per stratum and dimension
+        assert np.array_equal(np.sort(np.floor(H[:, j] * 1000).astype(int)), np.arange(1000))
+    np.random.seed(1111)
+    assert np.array_equal(P.lhs(3, 1000), H)                      # reproducible from np.random.seed like pyDOE
+    # published pyDOE _lhsclassic call order: one rand(samples, n), then one permutation per column
+    np.random.seed(7)
+    u = np.random.rand(50, 2); cut = np.linspace(0, 1, 51)
+    pts = u * (cut[1:] - cut[:-1])[:, None] + cut[:-1, None]
+    exp = np.stack([pts[np.random.permutation(50), j] for j in range(2)], 1)
+    np.random.seed(7)
+    assert np.array_equal(P.lhs(2, 50), exp)
+    G = P.lhs(3, 64, rng=np.random.default_rng(0))
+    assert np.array_equal(np.sort(np.floor(G[:, 1] * 64).astype(int)), np.arange(64))
+
+
+def test_vectorised_deletions_and_distance_targets_match_the_loops():
+    rng = np.random.default_rng(3)
+    X = rng.uniform([0, 0, 0], [.5, .5, 10], (2000, 3))
+    X[:5, :2] = [[0.1, 0.0], [0.0, 0.1], [0.06, 0.08], [0.0, 0.0], [0.5, 0.5]]       # points on / inside the hole edge
+    np.testing.assert_array_equal(P.DelHolePT(X), O.DelHolePT(X))
+    np.testing.assert_array_equal(P.GenDist(X), O.GenDist(X))
+    Y = rng.uniform([-15, -15, 0], [15, 15, 14], (2000, 3))
+    Y[:3, :2] = [[2.0, 0.0], [0.0, -2.0], [1.2, 1.6]]
+    np.testing.assert_array_equal(P.DelSrcPT(Y, 0, 0, 2.0), O.DelSrcPT(Y, 0, 0, 2.0))
+    np.testing.assert_array_equal(P.DelSrcPT(Y, 0, 0, 2.0, strict=True), O.DelSrcPT(Y, 0, 0, 2.0, strict=True))
+    assert len(O.DelSrcPT(Y, 0, 0, 2.0)) > len(O.DelSrcPT(Y, 0, 0, 2.0, strict=True))   # the two scripts differ on the circle itself
+    np.testing.assert_allclose(P.GenDist_confined(Y), O.GenDist_confined(Y), rtol=1e-15, atol=0)
+
+
+def test_grids_sources_and_default_point_sets():
+    x, y, t = P.GenDistPt(0, 0.5, 0, 0.5, 0, 10, 0, 0, 0.1, num_surf_pt=40, num=21, num_t=21)
+    nxy = (21 * 21 - int((np.hypot(*np.meshgrid(np.linspace(0, .5, 21), np.linspace(0, .5, 21))) < 0.1).sum())) + 40
+    assert x.shape == (nxy * 21, 1) and t.min() == 0 and t.max() == 10
+    xx, yy = P.GenHoleSurfPT(0, 0, 0.1, 83)
+    np.testing.assert_allclose(np.hypot(xx, yy), 0.1, rtol=1e-14)
+    assert xx[0, 0] == 0.1 and abs(xx[-1, 0]) < 1e-16
+    cx, cy = P.GenCirclePT(15, 15, 2, 200)
+    np.testing.assert_allclose(np.hypot(cx - 15, cy - 15), 2, rtol=1e-14)
+    g = P.CartGrid(-15, 15, -15, 15, 0, 16, 5, 3)
+    assert g[0].shape == (75, 1) and set(np.unique(g[2])) == {0.0, 8.0, 16.0}
+    assert P.plate_traction(np.array([0.0, 2.5, 5.0])).round(12).tolist() == [0.0, 1.0, 0.0]      # plate:923-926
+    assert abs(P.ricker(np.array([3.0]))[0] + 1.0) < 1e-15                                        # -Amp at t = ts (semi:726)
+    sets = P.plate_point_sets(rng=np.random.default_rng(1), scale=0.02)
+    assert sets['HOLE'].shape == (83 * 120, 3) and sets['RT'].shape[1] == 4 and sets['DIST'].shape[1] == 8
+    assert (np.hypot(sets['IC'][:, 0], sets['IC'][:, 1]) > 0.1).all() and (sets['IC'][:, 2] == 0).all()
+    w = P.semi_point_sets(rng=np.random.default_rng(2), scale=0.02)
+    assert w['SRC'].shape == (150 * 215, 5) and (np.hypot(w['Collo'][:, 0], w['Collo'][:, 1]) >= 2.0).all()
+    assert (w['UP'][:, 1] == 15.0).all() and (w['IC'][:, 2] == 0).all()
+    a = np.arange(12.).reshape(6, 2); b = a.copy()
+    P.shuffle(a, rng=np.random.default_rng(0))
+    assert sorted(map(tuple, a)) == sorted(map(tuple, b)) and not np.array_equal(a, b)
+
+
+def test_fem_metrics():
+    ref = [np.array([[1.0], [2.0], [2.0]]), np.array([[0.0], [3.0], [4.0]])]
+    pred = [r * 1.01 for r in ref]
+    m = P.fem_metrics(pred, ref, names=('u', 'v'))
+    assert abs(m['u'] - 0.01) < 1e-12 and abs(m['v'] - 0.01) < 1e-12
