@@ -1,5 +1,6 @@
 """Run on the GPU box: pins tcgen05 descriptor / layout conventions with exact integer GEMMs (see csrc/umma_probe.cu).
-Prints PASS/FAIL per hypothesis; tests/test_gpu_umma_probe.py asserts the ones the engine relies on."""
+Prints PASS/FAIL per hypothesis (one process each: a faulting descriptor must not take the others down);
+tests/test_gpu_umma_probe.py asserts the conventions the tensor-core engine relies on."""
 import ctypes as C
 import os
 import sys
