@@ -170,6 +170,22 @@ int pe_forward_jets(const pe_plan *plan, int K, const float *d_points, int ld, i
                     const float *in_scale, const float *in_shift,
                     const float *d_params, float *d_out, void *stream);
 
+/* ---------------------------------------------------------------- device-resident L-BFGS
+ * Vector algebra of the limited-memory BFGS driver that replaces the SciPy round trip of
+ * ScipyOptimizerInterface.minimize (plate:240-247, 522-525; semi:151-156; conf:263-268).  All vectors are
+ * padded parameter vectors of length n = pe_plan_param_count_padded (pads stay zero); S, Y are [m][n] ring
+ * buffers (m = maxcor <= 64); d_state = m + 3 floats: [gamma | rho_0..rho_{m-1} | y.s | y.y of the last pair]. */
+/* d_dir = -H d_g by the two-loop recursion over the `count` newest pairs; `head` = slot of the newest pair. */
+int pe_lbfgs_direction(int n, int m, int count, int head, const float *d_g, const float *d_S, const float *d_Y,
+                       const float *d_state, float *d_dir, void *stream);
+/* slot `head` <- (s, y) = (x - x_prev, g - g_prev); updates rho[head] and gamma in d_state (rho = 0 when y.s <= 0). */
+int pe_lbfgs_store_pair(int n, int m, int head, const float *d_x, const float *d_xprev, const float *d_g,
+                        const float *d_gprev, float *d_S, float *d_Y, float *d_state, void *stream);
+/* d_out = d_x + alpha * d_d (the line-search trial point, written straight into the parameter buffer). */
+int pe_vec_axpy(int n, float *d_out, const float *d_x, float alpha, const float *d_d, void *stream);
+/* d_res[0] = a . b (double accumulation), d_res[1] = max |a_i| (the projected-gradient norm of the pgtol test). */
+int pe_vec_dot_max(int n, const float *d_a, const float *d_b, float *d_res, void *stream);
+
 /* ---------------------------------------------------------------- debug / profiling */
 /* Per-phase cycle counters of the tensor-core residual kernel: d_counters16 = 16 device uint64 (or NULL to switch off);
  * CTA 0 / thread 0 accumulates clock64 deltas per phase (tests/tc_phase_profile.py, profiles/r1_tc3_phase_cycles.txt). */

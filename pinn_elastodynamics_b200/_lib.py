@@ -62,6 +62,10 @@ SYMBOLS = [
     ('pe_reduce_adam', _i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     ('pe_forward_fields', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp, _vp, _vp]),
     ('pe_forward_jets', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp]),
+    ('pe_lbfgs_direction', _i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ('pe_lbfgs_store_pair', _i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ('pe_vec_axpy', _i, [_i, _vp, _vp, _f, _vp, _vp]),
+    ('pe_vec_dot_max', _i, [_i, _vp, _vp, _vp, _vp]),
     ('pe_debug_set_tc_profile', None, [_vp]),
 ]
 

@@ -307,7 +307,10 @@ resid_simt_kernel(const PeResidArgs args) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { acc[r][2 * c] = acc2[r][c].x; acc[r][2 * c + 1] = acc2[r][c].y; }
+                        for (int c = 0; c < 4; ++c) {     // pad columns (j >= dout) of the padded layout keep a zero gradient
+                            acc[r][2 * c] = (j0 + 2 * c < dout) ? acc2[r][c].x : 0.f;
+                            acc[r][2 * c + 1] = (j0 + 2 * c + 1 < dout) ? acc2[r][c].y : 0.f;
+                        }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int i = i0 + r;

@@ -15,6 +15,7 @@ train() calls (graph-level slots); each train_bfgs call restarts L-BFGS memory; 
 """
 from __future__ import annotations
 
+import ctypes as C
 import pickle
 
 import numpy as np
@@ -22,6 +23,7 @@ import torch
 
 from . import _lib as L
 from .engine import LossEngine, Network
+from .linesearch import strong_wolfe
 
 
 def xavier_init_lists(layers, rng):
@@ -177,7 +179,9 @@ class _Base:
         return [(int(i * N / batch_num), int((i + 1) * N / batch_num)) for i in range(batch_num)]
 
     # ---- L-BFGS-B through SciPy, as tf.contrib.opt.ScipyOptimizerInterface does (plate:240-247,522-525)
-    def _bfgs(self, options, callback, engine=None, net=None, total=None, shown=None):
+    bfgs_driver = 'scipy'          # 'scipy': SciPy's L-BFGS-B exactly as the reference drives it; 'gpu': device-resident L-BFGS
+
+    def _bfgs(self, options, callback, engine=None, net=None, total=None, shown=None, driver=None):
         """total(terms) is the minimised scalar; shown(terms) is what the reference passes to loss_callback
         (`fetches`, e.g. the unscaled loss_DIST while 1000*loss_DIST is minimised, plate:220,543)."""
         import scipy.optimize
@@ -185,6 +189,12 @@ class _Base:
         net = net or self.uv_net
         total = total or self._total
         shown = shown or total
+        driver = driver or dict(options).pop('driver', None) or self.bfgs_driver
+        if driver == 'gpu':
+            return self._bfgs_gpu({k: v for k, v in dict(options).items() if k != 'driver'}, callback, engine, net, total, shown)
+        if driver != 'scipy':
+            raise ValueError(f"bfgs driver {driver!r}: 'scipy' or 'gpu'")
+        options = {k: v for k, v in dict(options).items() if k != 'driver'}
 
         def fun(x):
             net.set_flat(x)
@@ -199,6 +209,95 @@ class _Base:
         res = scipy.optimize.minimize(fun, x0, jac=True, method='L-BFGS-B', options=dict(options))
         net.set_flat(res.x)
         return res
+
+    # ---- device-resident L-BFGS: same objective, same evaluation kernels, same options dictionary as
+    # the SciPy path, but x, g and the (S, Y) history stay in HBM (csrc/pe_lbfgs.cu) and the host only reads the
+    # scalars the line search branches on (8 loss terms, g.d, max|g|: one 40-byte D2H per evaluation).
+    def _bfgs_gpu(self, options, callback, engine, net, total, shown):
+        """Unconstrained L-BFGS (the reference passes no bounds, so L-BFGS-B's projection is inactive: plate:240-247) with
+        a strong-Wolfe line search (sufficient decrease 1e-3, curvature 0.9: the constants of L-BFGS-B's lnsrlb).
+        Honours maxiter / maxfun / maxcor / maxls / ftol / gtol with SciPy's meaning and returns an OptimizeResult.
+        Iterates are not bit-identical to SciPy's (different line search, fp32 vectors); tests compare the reached loss."""
+        import scipy.optimize
+        lib, n, dev = engine.lib, net.Pp, self.device
+        m = max(1, min(int(options.get('maxcor', 10)), 64))
+        maxiter = int(options.get('maxiter', 15000)); maxfun = int(options.get('maxfun', 15000))
+        maxls = int(options.get('maxls', 20)); ftol = float(options.get('ftol', 2.2204460492503131e-09))
+        gtol = float(options.get('gtol', 1e-5))
+        c1, c2 = 1e-3, 0.9
+        f32 = dict(dtype=torch.float32, device=dev)
+        S = torch.zeros(m, n, **f32); Y = torch.zeros(m, n, **f32); state = torch.zeros(m + 3, **f32)
+        xprev = torch.empty(n, **f32); gprev = torch.empty(n, **f32); d = torch.zeros(n, **f32)
+        scal = torch.zeros(10, **f32)
+        if not engine._built:
+            engine.build()
+        x, g = net.params, engine.out[:n]
+        st = engine._stream
+        P = lambda t: C.c_void_p(t.data_ptr())
+        nfev = 0
+
+        def scalars(other):
+            """(terms, g.other, max|g|) of the current evaluation: one small D2H."""
+            scal[:8].copy_(engine.out[n:n + 8])
+            L.check(lib.pe_vec_dot_max(n, P(g), P(other), P(scal[8:]), st()), 'pe_vec_dot_max')
+            h = scal.cpu().numpy().astype(np.float64)
+            return h[:8], float(h[8]), float(h[9])
+
+        def feval(other):
+            nonlocal nfev
+            engine.evaluate()
+            nfev += 1
+            terms, gd, gmax = scalars(other)
+            callback(shown(terms))
+            return total(terms), gd, gmax
+
+        def phi(alpha):
+            L.check(lib.pe_vec_axpy(n, P(x), P(xprev), float(alpha), P(d), st()), 'pe_vec_axpy')
+            return feval(d)
+
+        f, gg, gmax = feval(g)
+        count, head, nit = 0, -1, 0
+        message, success = 'STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT', False
+        while nit < maxiter:
+            if gmax <= gtol:
+                message, success = 'CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL', True
+                break
+            if nfev >= maxfun:
+                message = 'STOP: TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT'
+                break
+            L.check(lib.pe_lbfgs_direction(n, m, count, max(head, 0), P(g), P(S), P(Y), P(state), P(d), st()), 'pe_lbfgs_direction')
+            _, dphi0, _ = scalars(d)
+            if not dphi0 < 0.0:
+                if count == 0:
+                    message = 'ABNORMAL: NOT A DESCENT DIRECTION'
+                    break
+                count = 0                                               # drop the history, restart from steepest descent
+                continue
+            xprev.copy_(x); gprev.copy_(g)
+            alpha0 = 1.0 if count > 0 else min(1.0, 1.0 / max(np.sqrt(gg), 1e-30))   # L-BFGS-B: first step 1/||d||
+            ok, alpha, f_new, _, gmax_new = strong_wolfe(phi, f, dphi0, alpha0, c1, c2, maxls, budget=lambda: maxfun - nfev)
+            if not ok:
+                x.copy_(xprev); g.copy_(gprev)
+                if nfev >= maxfun:
+                    message = 'STOP: TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT'
+                    break
+                if count == 0:
+                    message = 'ABNORMAL: LINE SEARCH FAILED'
+                    break
+                count = 0
+                _, gg, gmax = scalars(g)
+                continue
+            head = (head + 1) % m
+            count = min(count + 1, m)
+            L.check(lib.pe_lbfgs_store_pair(n, m, head, P(x), P(xprev), P(g), P(gprev), P(S), P(Y), P(state), st()), 'pe_lbfgs_store_pair')
+            nit += 1
+            rel = (f - f_new) / max(abs(f), abs(f_new), 1.0)
+            f, gmax = f_new, gmax_new
+            if rel <= ftol:
+                message, success = 'CONVERGENCE: RELATIVE REDUCTION OF F <= FTOL', True
+                break
+        return scipy.optimize.OptimizeResult(x=net.get_flat().astype(np.float64), fun=f, nit=nit, nfev=nfev, message=message,
+                                             success=success, status=0 if success else 1)
 
     def callback(self, loss):
         self.count = self.count + 1
