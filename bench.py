@@ -305,6 +305,7 @@ def main():
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'defected plate F5 (plane stress), 5x50 tanh mixed-variable net, {args.points} collocation pts/GPU + {HOLE.shape[0] // world} hole pts/GPU, Adam lr 5e-4 (BASELINE configs[1])',
                        'net': LAYERS, 'global_collocation_points': n_total, 'engine': args.engine, 'parallelism': f'dp{world} (index-sharded points, 1 all-reduce of [grad|terms] per step)',
+                       'allreduce': None if world == 1 else ('in-kernel over NVLink peer memory, fused with slot reduction and Adam (pe_reduce_peer)' if eng.comm is not None else 'NCCL (reduce -> all_reduce -> Adam)'),
                        'l2': 'flushed between timed steps (256 MiB memset outside the per-step event pairs)'},
             'clocks': clocks,
             'gpu_launches': launches,

@@ -170,6 +170,27 @@ int pe_forward_jets(const pe_plan *plan, int K, const float *d_points, int ld, i
                     const float *in_scale, const float *in_shift,
                     const float *d_params, float *d_out, void *stream);
 
+/* ---------------------------------------------------------------- multi-GPU step over NVLink peer memory
+ * The reference is single-device; data parallelism here shards every point set by index and needs ONE sum of
+ * [grad | terms] per step.  Instead of reduce -> ncclAllReduce -> Adam (three launches and NCCL's latency) the ranks of one
+ * node exchange their slices through IPC-mapped peer memory inside one kernel: slot reduction, push to all peers,
+ * flag wait, rank-ordered sum (bit-identical on every rank), Adam.  Host protocol: every rank calls pe_comm_create,
+ * all-gathers the 64-byte handles (any transport), calls pe_comm_connect, then pe_reduce_peer once per step in lockstep.
+ * Teardown: every rank calls pe_comm_disconnect (unmaps the peers), then a barrier, then pe_comm_destroy (frees its region). */
+#define PE_MAX_PEERS 8
+#define PE_IPC_HANDLE_BYTES 64
+typedef struct pe_comm pe_comm;
+pe_comm *pe_comm_create(const pe_plan *plan, int rank, int world, unsigned char *handle_out /* 64 bytes */);
+int pe_comm_connect(pe_comm *comm, const unsigned char *all_handles /* world x 64 bytes, rank order */);
+/* non-zero if a kernel gave up waiting for a peer (about 20 s); synchronises the device. */
+int pe_comm_error(pe_comm *comm);
+void pe_comm_disconnect(pe_comm *comm);
+void pe_comm_destroy(pe_comm *comm);
+/* pe_reduce_partials + all-reduce (+ pe_adam_step when d_params != NULL) in one launch; arguments as pe_reduce_adam. */
+int pe_reduce_peer(const pe_plan *plan, pe_comm *comm, const float *d_grad_partials, const float *d_term_partials,
+                   int n_slots, float *d_out, float *d_terms_copy, float *d_params, float *d_m, float *d_v, int *d_step,
+                   float lr, float beta1, float beta2, float eps, void *stream);
+
 /* ---------------------------------------------------------------- device-resident L-BFGS
  * Vector algebra of the limited-memory BFGS driver that replaces the SciPy round trip of
  * ScipyOptimizerInterface.minimize (plate:240-247, 522-525; semi:151-156; conf:263-268).  All vectors are

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(HERE, 'libpinn_elasto.so')
 PE_MAX_LAYERS = 16
 PE_MAX_TERMS = 8
 PE_MAX_COLS = 8
+PE_MAX_PEERS = 8
+PE_IPC_HANDLE_BYTES = 64
 PE_TILE_POINTS = 32
 PE_TC_TILE = 128
 
@@ -62,6 +64,12 @@ SYMBOLS = [
     ('pe_reduce_adam', _i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     ('pe_forward_fields', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp, _vp, _vp]),
     ('pe_forward_jets', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp]),
+    ('pe_comm_create', _vp, [_vp, _i, _i, _vp]),
+    ('pe_comm_connect', _i, [_vp, _vp]),
+    ('pe_comm_error', _i, [_vp]),
+    ('pe_comm_disconnect', None, [_vp]),
+    ('pe_comm_destroy', None, [_vp]),
+    ('pe_reduce_peer', _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     ('pe_lbfgs_direction', _i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     ('pe_lbfgs_store_pair', _i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ('pe_vec_axpy', _i, [_i, _vp, _vp, _f, _vp, _vp]),

@@ -2,6 +2,7 @@
 // Replaces tf.train.AdamOptimizer(...).minimize's ApplyAdam nodes (PlateHoleQuarter/train/train.py:249-250)
 // and the tf.reduce_mean scalar reductions (train.py:187-217).  See SURVEY.md A.3 for the epsilon convention.
 #include "pe_common.cuh"
+#include <cstring>
 
 namespace {
 
@@ -129,6 +130,105 @@ __global__ void reduce_adam_kernel(const float* __restrict__ gp, const float* __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Slot reduction + all-reduce over NVLink peer memory + Adam in ONE kernel (multi-GPU step).
+// Every rank owns a region [2 buffers][world sources][n = total + 8 floats] + arrival flags, mapped into all peers (CUDA IPC).
+// Block b of rank r: (1) sums its 128-float slice over the gradient-partial slots, (2) PUSHES the slice into source row r of every
+// peer's region (fire-and-forget NVLink stores), fences, and raises flag[r][b] = seq in every peer, (3) polls its LOCAL flags
+// [q][b] for all q, (4) adds the `world` rows in rank order -- the same order on every rank, so all ranks hold bit-identical
+// gradients -- and applies Adam to its slice.  A block only ever waits for the same-index block of its peers, so no grid-wide
+// co-residency is needed.  Buffers alternate with seq: a rank can be at most one step ahead of a peer (it needs the peer's
+// flags of step s to finish step s), so buffer s&1 is never overwritten while still being read.
+struct PeerArgs {
+    float* data[PE_MAX_PEERS];
+    unsigned int* flags[PE_MAX_PEERS];
+    int* err;
+    int rank, world, n, n_cta;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded wait (about 20 s of SM clock): a dead peer must not hang the GPU for good; the error word is read by pe_comm_error
+__device__ __forceinline__ void wait_flag(const unsigned int* p, unsigned int seq, int* err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - seq) < 0) {
+        if (*reinterpret_cast<volatile int*>(err)) break;              // an earlier wait already failed: do not stall every later step
+        if (clock64() - t0 > 40000000000LL) { atomicExch(err, 1); break; }
+    }
+}
+
+__global__ void reduce_peer_adam_kernel(const float* __restrict__ gp, const float* __restrict__ tp, int n_slots, int total, float* __restrict__ out,
+                                        float* __restrict__ tcopy, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                                        int* __restrict__ d_step, unsigned int* __restrict__ ticket, float lr, float b1, float b2, float eps,
+                                        PeerArgs pa, unsigned int seq, int do_adam) {
+    int step = 0;
+    float lr_t = 0.f;
+    if (do_adam) { step = *reinterpret_cast<volatile int*>(d_step) + 1; lr_t = adam_lr_t(step, lr, b1, b2); }
+    const int i4 = blockIdx.x * RED_TX + threadIdx.x;
+    const bool in_range = i4 < (total >> 2);
+    const float4 s = sum_slots4(gp, n_slots, total, i4, in_range);
+    const int buf = (int)(seq & 1u);
+    const int lane = threadIdx.x;
+    const size_t row = (size_t)pa.n;
+    if (threadIdx.y == 0) {
+        if (in_range)
+            for (int p = 0; p < pa.world; ++p)
+                reinterpret_cast<float4*>(pa.data[p] + ((size_t)buf * pa.world + pa.rank) * row)[i4] = s;
+        __threadfence_system();
+        __syncwarp();
+        if (lane < pa.world) st_release_sys(pa.flags[lane] + (size_t)pa.rank * (pa.n_cta + 1) + blockIdx.x, seq);
+        if (lane < pa.world) wait_flag(pa.flags[pa.rank] + (size_t)lane * (pa.n_cta + 1) + blockIdx.x, seq, pa.err);
+        __syncwarp();
+        if (in_range) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < pa.world; ++q) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(pa.data[pa.rank] + ((size_t)buf * pa.world + q) * row) + i4);
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            }
+            reinterpret_cast<float4*>(out)[i4] = g;
+            if (do_adam) {
+                float4 p = reinterpret_cast<float4*>(params)[i4];
+                float4 mm = reinterpret_cast<float4*>(m)[i4];
+                float4 vv = reinterpret_cast<float4*>(v)[i4];
+                adam4(p, g, mm, vv, lr_t, b1, b2, eps);
+                reinterpret_cast<float4*>(params)[i4] = p;
+                reinterpret_cast<float4*>(m)[i4] = mm;
+                reinterpret_cast<float4*>(v)[i4] = vv;
+            }
+        }
+    } else if (blockIdx.x == 0 && threadIdx.y == 1) {          // the 8 loss terms ride the same exchange (flag column n_cta)
+        float st = 0.f;
+        if (lane < PE_MAX_TERMS) {
+            for (int k = 0; k < n_slots; ++k) st += __ldcg(tp + (size_t)k * PE_MAX_TERMS + lane);
+            for (int p = 0; p < pa.world; ++p) pa.data[p][((size_t)buf * pa.world + pa.rank) * row + total + lane] = st;
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < pa.world) st_release_sys(pa.flags[lane] + (size_t)pa.rank * (pa.n_cta + 1) + pa.n_cta, seq);
+        if (lane < pa.world) wait_flag(pa.flags[pa.rank] + (size_t)lane * (pa.n_cta + 1) + pa.n_cta, seq, pa.err);
+        __syncwarp();
+        if (lane < PE_MAX_TERMS) {
+            float g = 0.f;
+            for (int q = 0; q < pa.world; ++q) g += __ldcg(pa.data[pa.rank] + ((size_t)buf * pa.world + q) * row + total + lane);
+            out[total + lane] = g;
+            if (tcopy) tcopy[lane] = g;
+        }
+    }
+    __syncthreads();
+    if (do_adam && threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) { *d_step = step; *ticket = 0u; __threadfence(); }
+    }
+}
+
 }  // namespace
 
 extern "C" int pe_reduce_partials(const pe_plan* plan, const float* d_grad_partials, const float* d_term_partials,
@@ -171,5 +271,107 @@ extern "C" int pe_reduce_adam(const pe_plan* plan, const float* d_grad_partials,
                                                              lr, beta1, beta2, eps);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("reduce_adam_kernel: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
+// ---------------------------------------------------------------- peer-memory communicator (single node, CUDA IPC)
+struct pe_comm {
+    int rank, world, n, n_cta;
+    size_t bytes, flags_off, err_off;
+    unsigned char* local;
+    unsigned char* peer[PE_MAX_PEERS];
+    unsigned int seq;
+    int connected;
+};
+
+extern "C" pe_comm* pe_comm_create(const pe_plan* plan, int rank, int world, unsigned char* handle_out) {
+    if (!plan || !handle_out || world < 2 || world > PE_MAX_PEERS || rank < 0 || rank >= world) {
+        pe_set_error("pe_comm_create: bad arguments (2 <= world <= %d)", PE_MAX_PEERS);
+        return nullptr;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == PE_IPC_HANDLE_BYTES, "IPC handle size");
+    pe_comm* c = new pe_comm();
+    c->rank = rank; c->world = world;
+    c->n = plan->lay.total + PE_MAX_TERMS;
+    c->n_cta = (plan->lay.total / 4 + RED_TX - 1) / RED_TX;
+    c->flags_off = sizeof(float) * 2 * (size_t)world * c->n;
+    c->err_off = c->flags_off + sizeof(unsigned int) * (size_t)world * (c->n_cta + 1);
+    c->bytes = ((c->err_off + 64 + (2u << 20) - 1) / (2u << 20)) * (2u << 20);          // whole 2 MiB pages: nothing else shares the IPC mapping
+    cudaError_t e = cudaMalloc(&c->local, c->bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->local, 0, c->bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
+    if (e != cudaSuccess) {
+        pe_set_error("pe_comm_create: %s", cudaGetErrorString(e));
+        if (c->local) cudaFree(c->local);
+        delete c;
+        return nullptr;
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    return c;
+}
+
+extern "C" int pe_comm_connect(pe_comm* c, const unsigned char* all_handles) {
+    if (!c || !all_handles) { pe_set_error("pe_comm_connect: null argument"); return 1; }
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) { c->peer[p] = c->local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)p * PE_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            pe_set_error("pe_comm_connect: cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            for (int q = 0; q < p; ++q) if (q != c->rank && c->peer[q]) { cudaIpcCloseMemHandle(c->peer[q]); c->peer[q] = nullptr; }
+            return 3;
+        }
+        c->peer[p] = static_cast<unsigned char*>(ptr);
+    }
+    c->connected = 1;
+    return 0;
+}
+
+extern "C" int pe_comm_error(pe_comm* c) {
+    if (!c) return 1;
+    int err = 0;
+    if (cudaMemcpy(&err, c->local + c->err_off, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (err) pe_set_error("peer all-reduce timed out waiting for a peer rank");
+    return err;
+}
+
+extern "C" void pe_comm_disconnect(pe_comm* c) {
+    if (!c || !c->connected) return;
+    for (int p = 0; p < c->world; ++p) if (p != c->rank && c->peer[p]) { cudaIpcCloseMemHandle(c->peer[p]); c->peer[p] = nullptr; }
+    c->connected = 0;
+}
+
+extern "C" void pe_comm_destroy(pe_comm* c) {
+    if (!c) return;
+    pe_comm_disconnect(c);
+    if (c->local) cudaFree(c->local);
+    delete c;
+}
+
+extern "C" int pe_reduce_peer(const pe_plan* plan, pe_comm* c, const float* d_grad_partials, const float* d_term_partials, int n_slots,
+                              float* d_out, float* d_terms_copy, float* d_params, float* d_m, float* d_v, int* d_step,
+                              float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!plan || !c || !c->connected) { pe_set_error("pe_reduce_peer: communicator not connected"); return 1; }
+    if (c->n != plan->lay.total + PE_MAX_TERMS) { pe_set_error("pe_reduce_peer: communicator was created for another plan"); return 1; }
+    PeerArgs pa;
+    for (int p = 0; p < c->world; ++p) {
+        pa.data[p] = reinterpret_cast<float*>(c->peer[p]);
+        pa.flags[p] = reinterpret_cast<unsigned int*>(c->peer[p] + c->flags_off);
+    }
+    pa.err = reinterpret_cast<int*>(c->local + c->err_off);
+    pa.rank = c->rank; pa.world = c->world; pa.n = c->n; pa.n_cta = c->n_cta;
+    c->seq += 1;
+    const int total = plan->lay.total;
+    dim3 bs(RED_TX, RED_TY);
+    const int do_adam = d_params != nullptr;
+    reduce_peer_adam_kernel<<<c->n_cta, bs, 0, (cudaStream_t)stream>>>(d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
+                                                                       d_params, d_m, d_v, d_step, do_adam ? reinterpret_cast<unsigned int*>(d_step + 1) : nullptr,
+                                                                       lr, beta1, beta2, eps, pa, c->seq, do_adam);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { pe_set_error("reduce_peer_adam_kernel: %s", cudaGetErrorString(e)); return 3; }
     return 0;
 }

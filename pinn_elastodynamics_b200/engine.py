@@ -7,6 +7,9 @@ hand-written sm_100a kernels behind include/pinn_elasto.h.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import socket
+import sys
 
 import numpy as np
 import torch
@@ -148,6 +151,8 @@ class LossEngine:
         self.terms = []
         self.out = torch.zeros(net.Pp + L.PE_MAX_TERMS, dtype=torch.float32, device=self.device)
         self._built = False
+        self.comm = None                       # peer-memory communicator (multi-GPU, one node): see _setup_comm
+        self._comm_tried = False
         self.launches = 0                      # kernels of this library launched so far (bench `gpu_launches`)
         self.kernel_events = None              # set to a dict name -> [(start, end)] to time each residual kernel with CUDA events
 
@@ -267,9 +272,64 @@ class LossEngine:
             self.launches += 1 if t.engine == L.ENGINE_SIMT_FP32 else 2      # tensor-core engine: operand-image prep + residual kernel
         return slots
 
+    # ---- multi-GPU: one-kernel slot reduction + all-reduce over NVLink peer memory (+ Adam); NCCL when it cannot be set up
+    def _setup_comm(self):
+        """Collective over the group (every rank reaches it at its first multi-rank evaluation).  The IPC handles travel over
+        torch.distributed; PE_PEER_ALLREDUCE=0 keeps the reduce -> NCCL all_reduce -> Adam path."""
+        self._comm_tried = True
+        dist = torch.distributed
+        if self.world < 2 or self.world > L.PE_MAX_PEERS or os.environ.get('PE_PEER_ALLREDUCE', '1') == '0':
+            return
+        if dist.get_backend(self.group) != 'nccl':
+            return
+        hosts = [None] * self.world
+        dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
+        handle = (C.c_ubyte * L.PE_IPC_HANDLE_BYTES)()
+        comm = self.lib.pe_comm_create(self.net.plan, self.rank, self.world, handle) if len(set(hosts)) == 1 else None
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        ok = torch.tensor([1 if comm else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            blob = torch.cat(allh).cpu().numpy().tobytes()
+            rc = self.lib.pe_comm_connect(comm, blob)
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.comm = comm
+        else:                                   # some rank could not export / map the region: all ranks use NCCL
+            if comm:
+                self.lib.pe_comm_destroy(comm)
+            if self.rank == 0:
+                msg = self.lib.pe_last_error()
+                print('[pinn_elasto] peer-memory all-reduce unavailable (%s): using NCCL' % (msg.decode() if msg else 'not one node'), file=sys.stderr)
+
+    def check_comm(self):
+        """Raise if a peer-memory reduction timed out (synchronises)."""
+        if self.comm is not None and self.lib.pe_comm_error(self.comm) != 0:
+            L.check(1, 'pe_reduce_peer')
+
+    def close(self):
+        """Collective teardown of the communicator (optional; the 2 MiB region otherwise lives until the process exits)."""
+        if self.comm is not None:
+            torch.cuda.synchronize(self.device)
+            self.lib.pe_comm_disconnect(self.comm)
+            torch.distributed.barrier(group=self.group)
+            self.lib.pe_comm_destroy(self.comm)
+            self.comm = None
+            self._comm_tried = False
+
     def evaluate(self, hist_row=None):
         """loss terms + full gradient into self.out = [grad (padded) | terms(8)] (all-reduced over ranks)."""
+        if self.world > 1 and not self._comm_tried:
+            self._setup_comm()
         slots = self.launch_terms()
+        if self.comm is not None:
+            L.check(self.lib.pe_reduce_peer(self.net.plan, self.comm, _ptr(self.gpart), _ptr(self.tpart), slots, _ptr(self.out), _ptr(hist_row),
+                                            None, None, None, None, 0.0, 0.0, 0.0, 0.0, self._stream()), 'pe_reduce_peer')
+            self.launches += 1
+            return self.out
         copy = hist_row if self.world == 1 else None
         L.check(self.lib.pe_reduce_partials(self.net.plan, _ptr(self.gpart), _ptr(self.tpart), slots, _ptr(self.out), _ptr(copy), self._stream()),
                 'pe_reduce_partials')
@@ -283,19 +343,28 @@ class LossEngine:
     def adam_step(self, lr, hist_row=None, beta1=0.9, beta2=0.999, eps=1e-8):
         """One Adam step (TF1 form).  hist_row receives the PRE-update loss terms of this step."""
         net = self.net
+        if self.world > 1 and not self._comm_tried:
+            self._setup_comm()
         if self.world == 1:
             slots = self.launch_terms()
             L.check(self.lib.pe_reduce_adam(net.plan, _ptr(self.gpart), _ptr(self.tpart), slots, _ptr(self.out), _ptr(hist_row),
                                             _ptr(net.params), _ptr(net.m), _ptr(net.v), _ptr(net.step),
                                             lr, beta1, beta2, eps, self._stream()), 'pe_reduce_adam')
             self.launches += 1
-        else:
+        elif self.comm is not None:             # slot reduction + peer-memory all-reduce + Adam: one launch
+            slots = self.launch_terms()
+            L.check(self.lib.pe_reduce_peer(net.plan, self.comm, _ptr(self.gpart), _ptr(self.tpart), slots, _ptr(self.out), _ptr(hist_row),
+                                            _ptr(net.params), _ptr(net.m), _ptr(net.v), _ptr(net.step),
+                                            lr, beta1, beta2, eps, self._stream()), 'pe_reduce_peer')
+            self.launches += 1
+        else:                                   # NCCL path: reduce -> all_reduce -> Adam
             self.evaluate(hist_row)
             L.check(self.lib.pe_adam_step(net.plan, _ptr(net.params), _ptr(self.out), _ptr(net.m), _ptr(net.v), _ptr(net.step),
                                           lr, beta1, beta2, eps, self._stream()), 'pe_adam_step')
             self.launches += 1
 
     def terms_host(self):
+        self.check_comm()
         return self.out[self.net.Pp:].cpu().numpy().astype(np.float64)
 
     def grad_compact_host(self):

@@ -164,6 +164,7 @@ class _Base:
                 for t, bb in zip(terms, bufs):
                     t.points = bb[0]
             eng.evaluate(hist[iters])                                  # terms after the last update
+            eng.check_comm()
             h = hist.cpu().numpy().astype(np.float64)
             if self.verbose:                                           # same lines as plate:499-501, printed after the
                 for it in range(0, iters, 10):                         # asynchronous loop has drained (no per-step host sync)

@@ -31,13 +31,13 @@ m.engine.evaluate()
 t0 = m.engine.terms_host().tolist(); g0 = m.engine.grad_compact_host().astype(float)
 curve = m.train(5, 5e-4)[3]
 if int(os.environ.get('RANK', '0')) == 0:
-    print('RESULT ' + json.dumps({'terms': t0, 'gnorm': float(np.linalg.norm(g0)), 'g': g0[::97].tolist(), 'curve': curve, 'params': m.uv_net.get_flat()[::97].astype(float).tolist()}))
+    print('RESULT ' + json.dumps({'peer': m.engine.comm is not None, 'terms': t0, 'gnorm': float(np.linalg.norm(g0)), 'g': g0[::97].tolist(), 'curve': curve, 'params': m.uv_net.get_flat()[::97].astype(float).tolist()}))
 if world > 1:
     dist.destroy_process_group()
 ''' % ROOT
 
 
-def _run(world, engine, tmp_path):
+def _run(world, engine, tmp_path, peer=True):
     f = tmp_path / 'w.py'
     f.write_text(WORKER)
     if world == 1:
@@ -45,7 +45,7 @@ def _run(world, engine, tmp_path):
     else:
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
                '--master-port', '29611', str(f), engine]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PE_PEER_ALLREDUCE='1' if peer else '0'))
     line = [l for l in r.stdout.splitlines() if l.startswith('RESULT ')]
     assert line, r.stdout[-2000:] + r.stderr[-2000:]
     return json.loads(line[0][7:])
@@ -56,7 +56,18 @@ def test_two_gpus_match_one(engine, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     a, b = _run(1, engine, tmp_path), _run(2, engine, tmp_path)
+    assert b['peer'], 'the one-kernel peer-memory all-reduce did not come up (CUDA IPC): the run fell back to NCCL'
     np.testing.assert_allclose(b['terms'][:3], a['terms'][:3], rtol=2e-6)
     np.testing.assert_allclose(b['g'], a['g'], rtol=1e-4, atol=1e-6 * a['gnorm'])
     np.testing.assert_allclose(b['curve'], a['curve'], rtol=1e-5)
     np.testing.assert_allclose(b['params'], a['params'], rtol=1e-5, atol=1e-7)
+
+
+def test_peer_memory_allreduce_equals_nccl_path(tmp_path):
+    """reduce + NVLink peer-memory exchange + Adam in one kernel (pe_reduce_peer) against reduce -> NCCL all_reduce -> Adam:
+    with 2 ranks both add the two partial sums once (a + b), so the trajectories agree bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    a, b = _run(2, 'tc3', tmp_path, peer=True), _run(2, 'tc3', tmp_path, peer=False)
+    assert a['peer'] and not b['peer']
+    assert a['terms'] == b['terms'] and a['g'] == b['g'] and a['curve'] == b['curve'] and a['params'] == b['params']

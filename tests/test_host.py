@@ -21,7 +21,7 @@ def _lib():
 def test_library_exports_every_declared_symbol():
     L, lib = _lib()
     hdr = open(os.path.join(ROOT, 'include', 'pinn_elasto.h')).read()
-    declared = set(re.findall(r'^(?:int|size_t|void|const char \*|pe_plan \*)\s*(pe_[a-z_0-9]+)\(', hdr, flags=re.M))
+    declared = set(re.findall(r'^(?:int|size_t|void|const char \*|pe_plan \*|pe_comm \*)\s*(pe_[a-z_0-9]+)\(', hdr, flags=re.M))
     assert declared, 'no declarations parsed'
     bound = {name for name, _, _ in L.SYMBOLS}
     assert declared == bound, (declared ^ bound)
