@@ -52,7 +52,10 @@ enum {
 enum {
     PE_ENGINE_SIMT_FP32 = 0,   /* fp32 FFMA kernels: parity anchor, any width */
     PE_ENGINE_TC_TF32X3 = 1,   /* tcgen05 tensor-core tiles, 3xTF32 split (fp32-parity mode) */
-    PE_ENGINE_TC_TF32 = 2      /* tcgen05 tensor-core tiles, single-pass TF32 (fast mode) */
+    PE_ENGINE_TC_TF32 = 2,     /* tcgen05 tensor-core tiles, single-pass TF32 (fast mode) */
+    PE_ENGINE_TCP_TF32X3 = 3,  /* second-generation tcgen05 engine (csrc/pe_tcp.cu): 3xTF32 split, weight-gradient phase as a
+                                  converter-warps / MMA-warp pipeline; PE_RES_F5 (K=5) and PE_RES_F7 (K=4) */
+    PE_ENGINE_TCP_TF32 = 4     /* same, single-pass TF32 */
 };
 
 typedef struct pe_plan pe_plan; /* host-side description of one network: dims, padded layout, launch config */
@@ -98,7 +101,8 @@ int pe_plan_weight_offset(const pe_plan *plan, int layer);  /* offset of W_l in 
 int pe_plan_bias_offset(const pe_plan *plan, int layer);
 int pe_plan_weight_ld(const pe_plan *plan, int layer);      /* padded row stride of W_l */
 /* does `engine` (PE_ENGINE_*) implement residual `kind` with K streams for this network?  The tensor-core engines
-   cover PE_RES_F5 with hidden widths <= 56; the SIMT engine covers everything. */
+   cover hidden widths <= 56: PE_ENGINE_TC_* the PE_RES_F5 term, PE_ENGINE_TCP_* PE_RES_F5 and PE_RES_F7; the SIMT
+   engine covers everything. */
 int pe_engine_supported(const pe_plan *plan, int kind, int K, int engine);
 /* number of CTAs (= gradient-partial slots) a launch over n points uses, and its scratch size in floats */
 int pe_plan_slots(const pe_plan *plan, int n_points, int K, int engine);
@@ -211,6 +215,10 @@ int pe_vec_dot_max(int n, const float *d_a, const float *d_b, float *d_res, void
 /* Per-phase cycle counters of the tensor-core residual kernel: d_counters16 = 16 device uint64 (or NULL to switch off);
  * CTA 0 / thread 0 accumulates clock64 deltas per phase (tests/tc_phase_profile.py, profiles/r1_tc3_phase_cycles.txt). */
 void pe_debug_set_tc_profile(unsigned long long *d_counters16);
+/* Same for the PE_ENGINE_TCP_* kernels (selects their profiling instantiation while non-NULL). */
+void pe_debug_set_tcp_profile(unsigned long long *d_counters16);
+/* PE_ENGINE_TCP_*: 1 (default) = pipelined weight-gradient phase, 0 = the serial phase order of PE_ENGINE_TC_* (A/B timing). */
+void pe_debug_set_tcp_pipeline(int on);
 
 #ifdef __cplusplus
 }

@@ -22,8 +22,9 @@ PE_TILE_POINTS = 32
 PE_TC_TILE = 128
 
 RES_F5, RES_F7, RES_COLS, RES_TRACTION, RES_DT = 0, 1, 2, 3, 4
-ENGINE_SIMT_FP32, ENGINE_TC_TF32X3, ENGINE_TC_TF32 = 0, 1, 2
-ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3': ENGINE_TC_TF32X3, 'tc1': ENGINE_TC_TF32}
+ENGINE_SIMT_FP32, ENGINE_TC_TF32X3, ENGINE_TC_TF32, ENGINE_TCP_TF32X3, ENGINE_TCP_TF32 = 0, 1, 2, 3, 4
+# 'tc3p' / 'tc1p': second-generation tcgen05 engine (csrc/pe_tcp.cu: pipelined weight-gradient phase, F5 and F7)
+ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3': ENGINE_TC_TF32X3, 'tc1': ENGINE_TC_TF32, 'tc3p': ENGINE_TCP_TF32X3, 'tc1p': ENGINE_TCP_TF32}
 
 
 class TermDesc(C.Structure):
@@ -75,6 +76,8 @@ SYMBOLS = [
     ('pe_vec_axpy', _i, [_i, _vp, _vp, _f, _vp, _vp]),
     ('pe_vec_dot_max', _i, [_i, _vp, _vp, _vp, _vp]),
     ('pe_debug_set_tc_profile', None, [_vp]),
+    ('pe_debug_set_tcp_profile', None, [_vp]),
+    ('pe_debug_set_tcp_pipeline', None, [_i]),
 ]
 
 _lib = None

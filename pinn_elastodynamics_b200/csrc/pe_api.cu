@@ -17,7 +17,10 @@ void pe_set_error(const char* fmt, ...) {
 
 int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st,
                        const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
+int pe_launch_resid_tcp(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
+                        const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 int pe_tc_supported(const pe_plan* plan, int K, int engine);
+int pe_tcp_supported(const pe_plan* plan, int K);
 int pe_tc_slots(const pe_plan* plan, int n_points);
 size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
 size_t pe_tc_image_floats(const pe_plan* plan);
@@ -102,11 +105,13 @@ extern "C" int pe_plan_weight_offset(const pe_plan* plan, int l) { return (plan 
 extern "C" int pe_plan_bias_offset(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.boff[l] : -1; }
 extern "C" int pe_plan_weight_ld(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.ldw[l] : -1; }
 
-static bool is_tc(int engine) { return engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32; }
+static bool is_tcp(int engine) { return engine == PE_ENGINE_TCP_TF32X3 || engine == PE_ENGINE_TCP_TF32; }
+static bool is_tc(int engine) { return engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32 || is_tcp(engine); }
 
 extern "C" int pe_engine_supported(const pe_plan* plan, int kind, int K, int engine) {
     if (!plan) return 0;
     if (engine == PE_ENGINE_SIMT_FP32) return 1;
+    if (is_tcp(engine)) return (kind == PE_RES_F5 || kind == PE_RES_F7) && pe_tcp_supported(plan, K);
     if (is_tc(engine)) return kind == PE_RES_F5 && pe_tc_supported(plan, K, engine);
     return 0;
 }
@@ -213,8 +218,8 @@ static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K,
         if (term2) { pe_set_error("fused point sets need a tensor-core engine"); return 1; }
         return pe_launch_resid_simt(plan, a, K, pe_plan_slots(plan, n_local, K, engine), (cudaStream_t)stream);
     }
-    if (engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32) {
-        if (!pe_engine_supported(plan, term->kind, K, engine)) { pe_set_error("tensor-core engine does not support this residual kind / network (F5, K=5, hidden widths <= 56)"); return 1; }
+    if (is_tc(engine)) {
+        if (!pe_engine_supported(plan, term->kind, K, engine)) { pe_set_error("tensor-core engine %d does not support this residual kind / network (F5 K=5 [TCP: or F7 K=4], hidden widths <= 56)", engine); return 1; }
         int n_eff = n_local;
         if (term2) {
             if (check_term(plan, term2, 1)) return 1;
@@ -222,6 +227,8 @@ static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K,
             if (term2->aux_k && !d_aux2) { pe_set_error("fused composite set needs d_aux2"); return 1; }
             n_eff = PE_TC_TILE * ((n_local + PE_TC_TILE - 1) / PE_TC_TILE + (n2_local + PE_TC_TILE - 1) / PE_TC_TILE);
         }
+        if (is_tcp(engine))
+            return pe_launch_resid_tcp(plan, a, K, engine == PE_ENGINE_TCP_TF32 ? 1 : 0, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
         return pe_launch_resid_tc(plan, a, K, engine, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
     }
     pe_set_error("unknown engine %d", engine);
