@@ -111,3 +111,34 @@ def test_models_require_cuda():
     import pinn_elastodynamics_b200 as pe
     with pytest.raises(Exception):
         pe.PINN(np.zeros((4, 3)), np.zeros((4, 3)), None, None, None, None, None, None, [3, 8, 5], None, None, None, None, verbose=False)
+
+
+def test_engine_support_matrix():
+    """which residual kinds / networks each engine takes (pe_engine_supported): the SIMT engine everything; the round-1 tcgen05
+    engine the F5 term with hidden widths <= 56; the pipelined tcgen05 engine F5 (K=5, 5 outputs) and F7 (K=4, 7 outputs)."""
+    L, lib = _lib()
+
+    def sup(layers, kind, K, engine):
+        dims = (C.c_int * len(layers))(*layers)
+        plan = lib.pe_plan_create(dims, len(layers), -1)
+        assert plan, lib.pe_last_error()
+        r = lib.pe_engine_supported(plan, kind, K, L.ENGINES[engine])
+        lib.pe_plan_destroy(plan)
+        return r
+    f5, f7, w100 = [3] + 5 * [50] + [5], [3] + 5 * [50] + [7], [3] + 8 * [100] + [7]
+    for eng in ('simt', 'tc3', 'tc1', 'tc3p', 'tc1p'):
+        assert sup(f5, L.RES_F5, 5, eng) == 1
+        assert sup(f5, L.RES_TRACTION, 1, eng) == (1 if eng == 'simt' else 0)      # data terms stay on the SIMT engine
+        assert sup(f7, L.RES_COLS, 1, eng) == (1 if eng == 'simt' else 0)
+    assert sup(f7, L.RES_F7, 4, 'simt') == 1
+    assert sup(f7, L.RES_F7, 4, 'tc3') == 0 and sup(f7, L.RES_F7, 4, 'tc3p') == 1 and sup(f7, L.RES_F7, 4, 'tc1p') == 1
+    assert sup(w100, L.RES_F7, 4, 'tc3p') == 0                                      # hidden width > 56: SIMT only
+    assert sup([3, 56, 56, 5], L.RES_F5, 5, 'tc3p') == 1 and sup([3, 57, 56, 5], L.RES_F5, 5, 'tc3p') == 0
+    assert sup([3, 50, 5], L.RES_F5, 5, 'tc3p') == 1                                # one hidden layer: FFMA first layer + tensor-core output layer
+    assert sup(f5, L.RES_F7, 4, 'tc3p') == 0 and sup(f7, L.RES_F5, 5, 'tc3p') == 0   # K / output count must match the formulation
+    # slots / scratch queries are engine-aware
+    dims = (C.c_int * len(f5))(*f5)
+    plan = lib.pe_plan_create(dims, len(f5), -1)
+    assert lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3p']) == lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3']) == 148
+    assert lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3p']) == lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3'])
+    lib.pe_plan_destroy(plan)
