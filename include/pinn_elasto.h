@@ -55,7 +55,11 @@ enum {
     PE_ENGINE_TC_TF32 = 2,     /* tcgen05 tensor-core tiles, single-pass TF32 (fast mode) */
     PE_ENGINE_TCP_TF32X3 = 3,  /* second-generation tcgen05 engine (csrc/pe_tcp.cu): 3xTF32 split, weight-gradient phase as a
                                   converter-warps / MMA-warp pipeline; PE_RES_F5 (K=5) and PE_RES_F7 (K=4) */
-    PE_ENGINE_TCP_TF32 = 4     /* same, single-pass TF32 */
+    PE_ENGINE_TCP_TF32 = 4,    /* same, single-pass TF32 */
+    PE_ENGINE_TCS_TF32X3 = 5,  /* third-generation tcgen05 engine (csrc/pe_tcs.cu): warp-specialised (8 epilogue warps + MMA/TMA issuer
+                                  warp), jet-stream groups pipelined through the forward pass, TMA-fed double-buffered weight images;
+                                  same terms and networks as PE_ENGINE_TCP_* */
+    PE_ENGINE_TCS_TF32 = 6     /* same, single-pass TF32 */
 };
 
 typedef struct pe_plan pe_plan; /* host-side description of one network: dims, padded layout, launch config */
@@ -101,8 +105,8 @@ int pe_plan_weight_offset(const pe_plan *plan, int layer);  /* offset of W_l in 
 int pe_plan_bias_offset(const pe_plan *plan, int layer);
 int pe_plan_weight_ld(const pe_plan *plan, int layer);      /* padded row stride of W_l */
 /* does `engine` (PE_ENGINE_*) implement residual `kind` with K streams for this network?  The tensor-core engines
-   cover hidden widths <= 56: PE_ENGINE_TC_* the PE_RES_F5 term, PE_ENGINE_TCP_* PE_RES_F5 and PE_RES_F7; the SIMT
-   engine covers everything. */
+   cover hidden widths <= 56: PE_ENGINE_TC_* the PE_RES_F5 term, PE_ENGINE_TCP_* / PE_ENGINE_TCS_* PE_RES_F5 and PE_RES_F7;
+   the SIMT engine covers everything. */
 int pe_engine_supported(const pe_plan *plan, int kind, int K, int engine);
 /* number of CTAs (= gradient-partial slots) a launch over n points uses, and its scratch size in floats */
 int pe_plan_slots(const pe_plan *plan, int n_points, int K, int engine);

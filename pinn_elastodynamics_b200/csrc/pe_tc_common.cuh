@@ -78,6 +78,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
 }
+// ---- warp-specialised kernels (pe_tcs.cu): named barrier over a subset of warps, 1-D bulk TMA global -> shared
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bytes: multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_global, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_global), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tm_ld4(uint32_t addr, float (&v)[4]) {
     uint32_t r0, r1, r2, r3;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));

@@ -126,12 +126,13 @@ def test_engine_support_matrix():
         lib.pe_plan_destroy(plan)
         return r
     f5, f7, w100 = [3] + 5 * [50] + [5], [3] + 5 * [50] + [7], [3] + 8 * [100] + [7]
-    for eng in ('simt', 'tc3', 'tc1', 'tc3p', 'tc1p'):
+    for eng in ('simt', 'tc3', 'tc1', 'tc3p', 'tc1p', 'tc3s', 'tc1s'):
         assert sup(f5, L.RES_F5, 5, eng) == 1
         assert sup(f5, L.RES_TRACTION, 1, eng) == (1 if eng == 'simt' else 0)      # data terms stay on the SIMT engine
         assert sup(f7, L.RES_COLS, 1, eng) == (1 if eng == 'simt' else 0)
     assert sup(f7, L.RES_F7, 4, 'simt') == 1
     assert sup(f7, L.RES_F7, 4, 'tc3') == 0 and sup(f7, L.RES_F7, 4, 'tc3p') == 1 and sup(f7, L.RES_F7, 4, 'tc1p') == 1
+    assert sup(f7, L.RES_F7, 4, 'tc3s') == 1 and sup(w100, L.RES_F7, 4, 'tc3s') == 0
     assert sup(w100, L.RES_F7, 4, 'tc3p') == 0                                      # hidden width > 56: SIMT only
     assert sup([3, 56, 56, 5], L.RES_F5, 5, 'tc3p') == 1 and sup([3, 57, 56, 5], L.RES_F5, 5, 'tc3p') == 0
     assert sup([3, 50, 5], L.RES_F5, 5, 'tc3p') == 1                                # one hidden layer: FFMA first layer + tensor-core output layer
