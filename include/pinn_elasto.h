@@ -221,6 +221,8 @@ int pe_vec_dot_max(int n, const float *d_a, const float *d_b, float *d_res, void
 void pe_debug_set_tc_profile(unsigned long long *d_counters16);
 /* Same for the PE_ENGINE_TCP_* kernels (selects their profiling instantiation while non-NULL). */
 void pe_debug_set_tcp_profile(unsigned long long *d_counters16);
+/* PE_ENGINE_TCS_*: d_counters32 = 32 device uint64: 0..15 phases of epilogue thread 0, 16..31 phases of the MMA/TMA issuer (CTA 0). */
+void pe_debug_set_tcs_profile(unsigned long long *d_counters32);
 /* PE_ENGINE_TCP_*: 1 (default) = pipelined weight-gradient phase, 0 = the serial phase order of PE_ENGINE_TC_* (A/B timing). */
 void pe_debug_set_tcp_pipeline(int on);
 

@@ -80,6 +80,7 @@ SYMBOLS = [
     ('pe_debug_set_tc_profile', None, [_vp]),
     ('pe_debug_set_tcp_profile', None, [_vp]),
     ('pe_debug_set_tcp_pipeline', None, [_i]),
+    ('pe_debug_set_tcs_profile', None, [_vp]),
 ]
 
 _lib = None

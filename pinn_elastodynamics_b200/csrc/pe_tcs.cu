@@ -66,7 +66,11 @@ struct TcsArgs {
     const float* aux2;
     int n2;
     float inv_n2;
+    unsigned long long* prof;   // PROF instantiation: 32 cycle counters (0..15 epilogue thread 0, 16..31 issuer) of CTA 0
 };
+
+// phase timing (PROF instantiations only): the calling thread adds the cycles since its previous mark to counter `slot`
+#define TCS_PROF(slot) do { if (PROF) { if (prof_on) { const long long now_ = clock64(); atomicAdd(args.prof + (slot), (unsigned long long)(now_ - prof_t)); prof_t = now_; } } } while (0)
 
 // MMAs of one layer GEMM for streams [k0, k0 + nk): K-steps interleaved across the streams of the call.  The K-step loops are
 // deliberately not unrolled: the issuing thread lives in the register-starved control warpgroup, and the few integer adds per
@@ -106,7 +110,7 @@ __device__ __forceinline__ void issue_streams(int k0, int nk, uint32_t tbase, ui
     }
 }
 
-template <int NS>
+template <int NS, bool PROF>
 __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs args) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int STASH_LAYER = NS * TC_STASH_STREAM;          // bytes per stashed layer
@@ -117,6 +121,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = lay.L;
     const int fast = args.fast;
+    const bool prof_on = PROF && args.prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 256);
+    long long prof_t = 0;
+    (void)prof_on; (void)prof_t;
     uint8_t* act = smem + S_ACT;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S_MISC + B_TMEM);
     float* coord = reinterpret_cast<float*>(smem + S_COORD);
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
             auto wait_act = [&](int g) { mbar_wait(bar_act + 8 * g, (pact >> g) & 1u); pact ^= 1u << g; };
             load_img(2);
             load_img(3);
+            if (PROF) prof_t = clock64();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 // ---------------------------------------------------------------- forward: layers 2..L, group by group
                 for (int l = 2; l <= L; ++l) {
@@ -189,18 +197,22 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     const int NF = (lay.d[l] <= 16) ? 16 : 64;
                     const int ksteps = (lay.d[l - 1] + 7) >> 3, kb = (lay.d[l - 1] + 15) >> 4;
                     wait_img(b);
+                    TCS_PROF(16);
 #pragma unroll 1
                     for (int g = 0; g < 3; ++g) {
                         wait_act(g);
+                        TCS_PROF(17 + 2 * g);
                         fence_after();
                         issue_streams(grp_first<NS>(g), grp_count<NS>(g), tbase, act_s, img_s0 + b * TC_IMG_SET, NF, ksteps, kb, fast);
                         mma_commit(bar_acc + 8 * g);
+                        TCS_PROF(18 + 2 * g);
                         if (g == 2) ++n_acc2;
                         if (g == 0 && l >= 3) {
                             // every MMA of layer l-1 precedes G0 of layer l in the pipe: once its last group is complete, its image
                             // buffer (= the buffer of image l+1) is free
                             mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
                             load_img(l + 1);
+                            TCS_PROF(23);
                         }
                     }
                 }
@@ -208,13 +220,16 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 for (int l = L; l >= 2; --l) {
                     const int dout = lay.d[l];
                     wait_img(0);
+                    TCS_PROF(24);
                     wait_act(0); wait_act(1); wait_act(2);
+                    TCS_PROF(25);
                     fence_after();
                     issue_streams(0, NS, tbase, act_s, img_s0, 64, (dout + 7) >> 3, (dout + 15) >> 4, fast);
                     mma_commit(bar_acc);
                     mma_commit(bar_acc + 8);
                     mma_commit(bar_acc + 16);
                     ++n_acc2;
+                    TCS_PROF(26);
                     // weight gradient: consumer side of the operand pipeline (see pe_tcp.cu)
                     const int NZ = (dout + 7) & ~7;
                     const uint32_t id2 = idesc_bf16_mn(64, 56 + NZ), id1 = idesc_bf16_mn(64, NZ);
@@ -240,7 +255,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     }
                     mma_commit(bar_dw);
                     ++n_dw;
+                    TCS_PROF(27);
                     mbar_wait(bar_dw, (n_dw - 1) & 1u);      // both buffers are free again
+                    TCS_PROF(28);
                     if (l > 2) {
                         mbar_expect_tx(bar_img, TC_IMG_SET);
                         tma_load_1d(img_s0, args.images + (size_t)(l - 2) * TC_IMG_LAYER + TC_IMG_SET, TC_IMG_SET, bar_img);
@@ -270,6 +287,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
 #pragma unroll
         for (int i = 0; i < PE_MAX_TERMS; ++i) { tsum[i] = 0.f; tsum2[i] = 0.f; }
 
+        if (PROF) prof_t = clock64();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const bool sec = tile >= ntiles_main;                          // tile of the fused primal-only set (CTA-uniform)
             const pe_term_desc& Tc = sec ? T2 : T;
@@ -330,6 +348,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 }
                 publish_fences();
                 publish(0); publish(1); publish(2);
+                TCS_PROF(0);
             }
             // ================================================================ forward: hidden layers 2..L-1, one stream group at a time
             for (int l = 2; l < L; ++l) {
@@ -345,6 +364,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 auto zero_pads = [&](int k) { if (h == 1) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); } };
                 // ---- G0: a = tanh(z_0 + b)
                 wait_acc(0);
+                TCS_PROF(1);
                 fence_after();
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
@@ -361,8 +381,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 zero_pads(0);
                 publish_fences();
                 publish(0);
+                TCS_PROF(2);
                 // ---- G1: a_x = s z_x, a_y = s z_y   (a re-read from this thread's own entries of the value plane)
                 wait_acc(1);
+                TCS_PROF(3);
                 fence_after();
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
@@ -385,8 +407,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 zero_pads(1); zero_pads(2);
                 publish_fences();
                 publish(1);
+                TCS_PROF(4);
                 // ---- G2: a_t = s z_t [, a_tt = s z_tt - 2 a a_t z_t]
                 wait_acc(2);
+                TCS_PROF(5);
                 fence_after();
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
@@ -413,12 +437,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 if (NS == 5) zero_pads(4);
                 publish_fences();
                 publish(2);
+                TCS_PROF(6);
             }
             // ================================================================ output layer L: residuals, loss partials, seeds
             {
                 const int dout = lay.d[L];
                 const float* bl = sbias + (L - 1) * 64;
                 wait_acc(0); wait_acc(1); wait_acc(2);
+                TCS_PROF(7);
                 fence_after();
                 if (h == 0) {
                     float Y[NS][PE_UJ];
@@ -462,6 +488,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 }
                 publish_fences();
                 publish(0); publish(1); publish(2);
+                TCS_PROF(8);
             }
             // ================================================================ reverse sweep, layers L .. 2
             for (int l = L; l >= 2; --l) {
@@ -521,7 +548,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 }
                 cvZ(0, 0);                                   // buffer 1 is free while the adjoint MMAs read buffer 0 / ACT / LO
                 cvZ(0, 1);
+                TCS_PROF(9);
                 wait_acc(0); wait_acc(1); wait_acc(2);       // adjoint MMAs done: buffer 0 and the LO columns are free now
+                TCS_PROF(10);
                 fence_after();
 #pragma unroll 1
                 for (int k = 0; k < NS; ++k) {
@@ -539,8 +568,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                         mbar_arrive(bar_full + 8 * X);
                     }
                 }
+                TCS_PROF(11);
                 mbar_wait(bar_dw, pdw);
                 pdw ^= 1u;
+                TCS_PROF(12);
                 fence_after();
                 {   // drain the dW tile: rows i = 16*quadrant + lane (lane < 16), row 63 = bias gradient; h selects the column half
                     const int quad = warp & 3;
@@ -569,6 +600,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                         for (int k = 0; k < 4; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
                     }
                 }
+                TCS_PROF(13);
                 // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
                 float4 Anext[NS];
 #pragma unroll
@@ -618,6 +650,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     publish_fences();
                     publish(0); publish(1); publish(2);
                 }
+                TCS_PROF(14);
             }
             // ================================================================ layer 1 gradient (3 x d1 + bias): FFMA, fixed-order reduce
             tm_wait_st();
@@ -661,6 +694,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 }
                 named_bar_sync(1, S_EPI);
             }
+            TCS_PROF(15);
         }
         // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem (fixed order)
         {
@@ -694,9 +728,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
-template <int NS>
+template <int NS, bool PROF>
 int launch_tcs(const TcsArgs& t, int slots, cudaStream_t st) {
-    auto kern = resid_tcs_kernel<NS>;
+    auto kern = resid_tcs_kernel<NS, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
     if (e != cudaSuccess) { pe_set_error("cudaFuncSetAttribute(resid_tcs, %d): %s", S_TOTAL, cudaGetErrorString(e)); return 2; }
     kern<<<slots, S_THREADS, S_TOTAL, st>>>(t);
@@ -709,6 +743,9 @@ int launch_tcs(const TcsArgs& t, int slots, cudaStream_t st) {
 
 size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
 
+static unsigned long long* g_tcs_prof = nullptr;
+extern "C" void pe_debug_set_tcs_profile(unsigned long long* d_counters32) { g_tcs_prof = d_counters32; }
+
 int pe_launch_resid_tcs(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2) {
     TcsArgs t;
@@ -720,14 +757,15 @@ int pe_launch_resid_tcs(const pe_plan* plan, const PeResidArgs& a, int K, int fa
         t.inv_n2 = 1.0f / (float)term2->n_global;
     }
     t.fast = fast;
+    t.prof = g_tcs_prof;
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
     uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
     t.images = images;
     tcp_prep_kernel<<<plan->lay.L * 16, 256, 0, st>>>(a.params, a.lay, images);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("tcp_prep_kernel: %s", cudaGetErrorString(e)); return 3; }
-    if (K == 5) return launch_tcs<5>(t, slots, st);
-    if (K == 4) return launch_tcs<4>(t, slots, st);
+    if (K == 5) return g_tcs_prof ? launch_tcs<5, true>(t, slots, st) : launch_tcs<5, false>(t, slots, st);
+    if (K == 4) return g_tcs_prof ? launch_tcs<4, true>(t, slots, st) : launch_tcs<4, false>(t, slots, st);
     pe_set_error("stream-pipelined tensor-core engine: K = %d not instantiated (4 or 5)", K);
     return 1;
 }

@@ -145,6 +145,45 @@ def prof(flush):
     lib.pe_debug_set_tcp_pipeline(1)
 
 
+TCS_NAMES = ['E: tile start + layer1 fwd', 'E: fwd wait ACC[G0]', 'E: fwd epilogue G0 (tanh)', 'E: fwd wait ACC[G1]', 'E: fwd epilogue G1 (x,y)', 'E: fwd wait ACC[G2]',
+             'E: fwd epilogue G2 (t,tt)', 'E: output layer wait', 'E: output/residual stage', 'E: rev sync + early conversions', 'E: rev wait adjoint MMAs',
+             'E: dW converter loop', 'E: wait dW MMAs', 'E: dW drain', 'E: bwd epilogue', 'E: layer1 grad',
+             'I: fwd wait image', 'I: fwd wait ACT[G0]', 'I: fwd issue G0', 'I: fwd wait ACT[G1]', 'I: fwd issue G1', 'I: fwd wait ACT[G2]', 'I: fwd issue G2',
+             'I: fwd wait prev layer + TMA', 'I: rev wait image', 'I: rev wait ACT', 'I: adjoint issue', 'I: dW loop (waits + issue)', 'I: wait dW done', '-', '-', '-']
+
+
+def profs(flush):
+    """per-phase cycles of the stream-pipelined kernel: epilogue thread 0 (E) and the MMA/TMA issuer (I) of CTA 0"""
+    for case in ('f5', 'f7'):
+        if case == 'f5':
+            layers = [3] + 5 * [50] + [5]
+            Collo, HOLE = bench.make_workload(50000)
+            m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine='tc3s')
+        else:
+            N = 200000
+            rng = np.random.default_rng(1111)
+            lb, ub = np.array([-15., -15, 0]), np.array([15., 15, 16])
+            P = rng.uniform(lb, ub, (N, 3))
+            IC = rng.uniform(lb, ub, (N // 12, 3)); UP = rng.uniform(lb, ub, (N // 10, 3))
+            SRC = np.concatenate([rng.uniform(lb, ub, (N // 5, 3)), rng.standard_normal((N // 5, 2)) * 0.1], 1)
+            layers = [3] + 5 * [50] + [7]
+            m = pe.DeepHPM(P, SRC, IC, UP, layers, lb, ub, verbose=False, engine='tc3s')
+        Ws, bs = R.xavier_params(layers, seed=1111); Ws[0] = Ws[0] * (0.1 if case == 'f7' else 1.0)
+        m.uv_net.set_weights(Ws, bs)
+        for _ in range(3):
+            m.engine.adam_step(5e-4)
+        pr = torch.zeros(32, dtype=torch.int64, device='cuda')
+        lib.pe_debug_set_tcs_profile(C.c_void_p(pr.data_ptr()))
+        steps = 10
+        for _ in range(steps):
+            m.engine.adam_step(5e-4)
+        torch.cuda.synchronize()
+        lib.pe_debug_set_tcs_profile(None)
+        p = pr.cpu().numpy().astype(np.float64) / steps
+        emit(case='profs', workload=case, E_total=float(p[:16].sum()), I_total=float(p[16:].sum()), phases={n: float(v) for n, v in zip(TCS_NAMES, p) if n != '-'})
+        del m
+
+
 if __name__ == '__main__':
     T0 = time.time()
     assert torch.cuda.is_available()
@@ -153,5 +192,5 @@ if __name__ == '__main__':
     what = sys.argv[1:] or ['f5', 'f7', 'prof']
     emit(case='start', what=what, device=torch.cuda.get_device_name(0))
     for w in what:
-        {'f5': f5, 'f7': f7, 'prof': prof}[w](flush)
+        {'f5': f5, 'f7': f7, 'prof': prof, 'profs': profs}[w](flush)
     emit(case='done')
