@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- collocation-point residual+grad evaluations / second per Adam step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine simt|tc3|tc1] [--points P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine tc3s|tc3p|tc3|simt|tc1s] [--points P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1], SURVEY.md 8d "Config 2"): defected plate, plane stress (E=20, mu=.25, rho=1),
@@ -35,8 +35,8 @@ S_WEIGHTS = sum(LAYERS[i] * LAYERS[i + 1] for i in range(len(LAYERS) - 1))     #
 FLOP_PER_POINT = 6 * 5 * S_WEIGHTS                                            # 6*K*S = 312,000
 METRIC = 'collocation-pt residual+grad evals/sec per Adam step'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures of
-# this command line at the default workload (profiles/r1_tc3_ncu_summary.txt, profiles/r1_simt_ncu_summary.txt); bytes
-TRAFFIC = {'tc3': 112.27e6 + 282.54e6, 'simt': 17.6e6 + 103.3e6}
+# the default workload (profiles/r1_tc3s_ncu_summary.txt, profiles/r1_tc3_ncu_summary.txt, profiles/r1_simt_ncu_summary.txt); bytes
+TRAFFIC = {'tc3': 112.27e6 + 282.54e6, 'tc3s': 120.89e6 + 285.23e6, 'simt': 17.6e6 + 103.3e6}
 
 
 def make_workload(n_c, seed=1111):
@@ -194,7 +194,7 @@ def main():
     ap.add_argument('--steps', type=int, default=1500)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--engine', default='tc3', help='tc3 = tcgen05 engine (fp32-parity split), tc3p = second-generation tcgen05 engine (pipelined weight gradient), simt = fp32 FFMA engine, tc1/tc1p = single-pass TF32')
+    ap.add_argument('--engine', default='tc3s', help='tc3s = warp-specialised, stream-pipelined tcgen05 engine (fp32-parity split; default), tc3 / tc3p = first / second generation tcgen05 engines (bit-identical results), simt = fp32 FFMA engine, tc1/tc1p/tc1s = single-pass TF32')
     ap.add_argument('--points', type=int, default=50000, help='collocation points per GPU')
     ap.add_argument('--ref-points', type=int, default=10000)
     ap.add_argument('--ref-steps', type=int, default=8)
@@ -311,7 +311,8 @@ def main():
             'gpu_launches': launches,
             'e2e': e2e,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': TRAFFIC.get(args.engine) if args.points == 50000 else None,
-                         'kernel': {'simt': 'resid_simt_kernel<5>', 'tc3p': 'resid_tcp_kernel<5> (tcgen05, pipelined dW)', 'tc1p': 'resid_tcp_kernel<5> (tcgen05, pipelined dW)'}.get(args.engine, 'resid_tc_kernel (tcgen05)') + ' (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
+                         'kernel': {'simt': 'resid_simt_kernel<5>', 'tc3p': 'resid_tcp_kernel<5> (tcgen05, pipelined dW)', 'tc1p': 'resid_tcp_kernel<5> (tcgen05, pipelined dW)',
+                                    'tc3s': 'resid_tcs_kernel<5> (tcgen05, warp-specialised)', 'tc1s': 'resid_tcs_kernel<5> (tcgen05, warp-specialised)'}.get(args.engine, 'resid_tc_kernel (tcgen05)') + ' (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
                          'flop_per_point': FLOP_PER_POINT,
                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in pk else 'fallback',
                          'fp32_ffma_peak_tflops': 148 * 128 * 2 * (clocks['sm_mhz'] or 1965.0) * 1e-6},

@@ -11,7 +11,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpinn_elasto.so')
+# PE_LIB_PATH: A/B timing of experimental builds of the same C ABI (tests/build_variant.sh); unset in normal use
+LIB_PATH = os.environ.get('PE_LIB_PATH') or os.path.join(HERE, 'libpinn_elasto.so')
 
 PE_MAX_LAYERS = 16
 PE_MAX_TERMS = 8
@@ -26,7 +27,8 @@ ENGINE_SIMT_FP32, ENGINE_TC_TF32X3, ENGINE_TC_TF32, ENGINE_TCP_TF32X3, ENGINE_TC
 # 'tc3p' / 'tc1p': second-generation tcgen05 engine (csrc/pe_tcp.cu: pipelined weight-gradient phase, F5 and F7)
 # 'tc3s' / 'tc1s': third generation (csrc/pe_tcs.cu: warp-specialised, stream groups pipelined through the forward pass)
 ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3': ENGINE_TC_TF32X3, 'tc1': ENGINE_TC_TF32, 'tc3p': ENGINE_TCP_TF32X3, 'tc1p': ENGINE_TCP_TF32,
-           'tc3s': ENGINE_TCS_TF32X3, 'tc1s': ENGINE_TCS_TF32}
+           'tc3s': ENGINE_TCS_TF32X3, 'tc1s': ENGINE_TCS_TF32,
+           'auto': ENGINE_TCS_TF32X3}      # fastest fp32-parity engine; terms it does not implement run on the SIMT engine (engine.py build())
 
 
 class TermDesc(C.Structure):

@@ -16,6 +16,7 @@ train() calls (graph-level slots); each train_bfgs call restarts L-BFGS memory; 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pickle
 
 import numpy as np
@@ -63,6 +64,12 @@ class _Base:
         self.uv_layers = list(uv_layers)
         self.verbose = verbose
         self.dtype = dtype
+        # engine: 'simt' (fp32 FFMA, any width: the parity anchor), 'auto' (= 'tc3s': tcgen05 engine for the collocation term where the
+        # net fits it -- hidden width <= 56, F5 / F7 -- and the SIMT engine for every other term), or an explicit name from
+        # _lib.ENGINES.  None reads $PE_ENGINE (default 'simt'), so a caller that keeps the reference's constructor signature can
+        # still pick the fast path.
+        if engine is None:
+            engine = os.environ.get('PE_ENGINE', 'simt')
         self._engine_name = engine
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.uv_net = Network(self.uv_layers, self.device)
@@ -344,7 +351,7 @@ class PINN(_Base):
     pre_options = dict(maxiter=20000, maxfun=20000, maxcor=50, maxls=50, ftol=0.00001 * np.finfo(float).eps)    # plate:223-237
 
     def __init__(self, Collo, HOLE, IC, LF, RT, UP, LW, DIST, uv_layers, dist_layers, part_layers, lb, ub,
-                 partDir='', distDir='', uvDir='', engine='simt', verbose=True, dtype=np.float64, composite=None):
+                 partDir='', distDir='', uvDir='', engine=None, verbose=True, dtype=np.float64, composite=None):
         self._init_common(uv_layers, lb, ub, engine, verbose, dtype)
         self.E, self.mu, self.rho, self.hole_r = 20.0, 0.25, 1.0, 0.1           # plate:39-42
         A = lambda a: None if a is None else np.asarray(a, dtype=np.float64)
@@ -483,7 +490,7 @@ class DeepHPM(_Base):
     term_names = ('loss_f_uv', 'loss_f_s', 'loss_IC', 'loss_SRC', 'loss_NB')
 
     def __init__(self, Collo, SRC, IC, UP, uv_layers, lb, ub, ExistModel=0, modelDir=None, variant='semi',
-                 engine='simt', verbose=True, dtype=None):
+                 engine=None, verbose=True, dtype=None):
         self.variant = variant
         if dtype is None:
             dtype = np.float32 if variant == 'inf' else np.float64
@@ -562,7 +569,7 @@ class DeepElasticWave(_Base):
     bfgs_options = dict(maxiter=100000, maxfun=100000, maxcor=50, maxls=50, ftol=1 * np.finfo(float).eps)   # conf:162-166
 
     def __init__(self, Collo, SRC, IC, FIXED, DIST, uv_layers, dist_layers, part_layers, lb, ub,
-                 uvDir='', partDir='', distDir='', engine='simt', verbose=True, dtype=np.float64):
+                 uvDir='', partDir='', distDir='', engine=None, verbose=True, dtype=np.float64):
         self._init_common(uv_layers, lb, ub, engine, verbose, dtype)
         self.E, self.mu, self.rho = 2.5, 0.25, 1.0
         A = lambda a: None if a is None else np.asarray(a, dtype=np.float64)
