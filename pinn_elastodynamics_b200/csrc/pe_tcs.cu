@@ -34,14 +34,6 @@
 #include "pe_device.cuh"
 #include "pe_tc_common.cuh"
 
-// experimental code paths (A/B builds: tests/build_variant.sh)
-#ifndef TCS_X2
-#define TCS_X2 0   // forward epilogues: one batched TMEM load per stream, chunk loops fully unrolled
-#endif
-#ifndef TCS_X3
-#define TCS_X3 0   // reverse epilogue: stash prefetch two chunks ahead
-#endif
-
 namespace {
 using namespace pe_dev;
 using namespace pe_tcc;
@@ -374,24 +366,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 wait_acc(0);
                 TCS_PROF(1);
                 fence_after();
-#if TCS_X2
-                {
-                    float zz[28];
-                    tm_ld28(tlane + TM_ACC + 28 * h, zz);
-                    tm_wait_ld();
-#pragma unroll
-                    for (int cc = 0; cc < 7; ++cc) {
-                        const int c = 7 * h + cc;
-                        float z[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = 4 * c + u;
-                            z[u] = (j < dout) ? tanh_branchfree(zz[4 * cc + u] + bl[j]) : 0.f;
-                        }
-                        store_stream(0, c, z);
-                    }
-                }
-#else
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
                     float z[4];
@@ -404,7 +378,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     }
                     store_stream(0, c, z);
                 }
-#endif
                 zero_pads(0);
                 publish_fences();
                 publish(0);
@@ -413,30 +386,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 wait_acc(1);
                 TCS_PROF(3);
                 fence_after();
-#if TCS_X2
-                {
-                    float zz1[28], zz2[28];
-                    tm_ld28(tlane + TM_ACC + 64 + 28 * h, zz1);
-                    tm_ld28(tlane + TM_ACC + 128 + 28 * h, zz2);
-                    tm_wait_ld();
-#pragma unroll
-                    for (int cc = 0; cc < 7; ++cc) {
-                        const int c = 7 * h + cc;
-                        const float4 a4 = *reinterpret_cast<const float4*>(act + c * TC_CH + p * 16);
-                        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-                        float z1[4], z2[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = 4 * c + u;
-                            const float s = fmaf(-av[u], av[u], 1.f);
-                            z1[u] = (j < dout) ? s * zz1[4 * cc + u] : 0.f;
-                            z2[u] = (j < dout) ? s * zz2[4 * cc + u] : 0.f;
-                        }
-                        store_stream(1, c, z1);
-                        store_stream(2, c, z2);
-                    }
-                }
-#else
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
                     const float4 a4 = *reinterpret_cast<const float4*>(act + c * TC_CH + p * 16);
@@ -455,7 +404,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     store_stream(1, c, z1);
                     store_stream(2, c, z2);
                 }
-#endif
                 zero_pads(1); zero_pads(2);
                 publish_fences();
                 publish(1);
@@ -464,33 +412,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 wait_acc(2);
                 TCS_PROF(5);
                 fence_after();
-#if TCS_X2
-                {
-                    float zz3[28], zz4[28];
-                    tm_ld28(tlane + TM_ACC + 192 + 28 * h, zz3);
-                    if (NS == 5) tm_ld28(tlane + TM_ACC + 256 + 28 * h, zz4);
-                    tm_wait_ld();
-#pragma unroll
-                    for (int cc = 0; cc < 7; ++cc) {
-                        const int c = 7 * h + cc;
-                        const float4 a4 = *reinterpret_cast<const float4*>(act + c * TC_CH + p * 16);
-                        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-                        float z3[4], z4[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = 4 * c + u;
-                            const float a = av[u];
-                            const float s = fmaf(-a, a, 1.f);
-                            const float zt = zz3[4 * cc + u];
-                            const float at = s * zt;
-                            z3[u] = (j < dout) ? at : 0.f;
-                            if (NS == 5) z4[u] = (j < dout) ? fmaf(s, zz4[4 * cc + u], -2.f * a * at * zt) : 0.f;
-                        }
-                        store_stream(3, c, z3);
-                        if (NS == 5) store_stream(4, c, z4);
-                    }
-                }
-#else
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
                     const float4 a4 = *reinterpret_cast<const float4*>(act + c * TC_CH + p * 16);
@@ -512,7 +433,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     store_stream(3, c, z3);
                     if (NS == 5) store_stream(4, c, z4);
                 }
-#endif
                 zero_pads(3);
                 if (NS == 5) zero_pads(4);
                 publish_fences();
@@ -680,35 +600,24 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                         for (int k = 0; k < 4; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
                     }
                 }
+                // both unit halves (warps w and w + 4) share the TMEM lanes: the tile must be drained by both before either overwrites
+                // the aliased lo-operand columns below
+                named_bar_sync(1, S_EPI);
                 TCS_PROF(13);
                 // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
                 float4 Anext[NS];
 #pragma unroll
                 for (int k = 0; k < NS; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (7 * h) * 512 + p * 4));
-#if TCS_X3
-                float4 Anext2[NS];
-#pragma unroll
-                for (int k = 0; k < NS; ++k) Anext2[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (7 * h + 1) * 512 + p * 4));
-#endif
 #pragma unroll 1
                 for (int c = 7 * h; c < 7 * h + 7; ++c) {
                     float ab[NS][4];
                     float4 Av[NS];
 #pragma unroll
                     for (int k = 0; k < NS; ++k) Av[k] = Anext[k];
-#if TCS_X3
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) Anext[k] = Anext2[k];
-                    if (c + 2 < 7 * h + 7) {
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) Anext2[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (c + 2) * 512 + p * 4));
-                    }
-#else
                     if (c + 1 < 7 * h + 7) {
 #pragma unroll
                         for (int k = 0; k < NS; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (c + 1) * 512 + p * 4));
                     }
-#endif
 #pragma unroll
                     for (int k = 0; k < NS; ++k) tm_ld4(tlane + TM_ACC + 64 * k + 4 * c, ab[k]);
                     tm_wait_ld();
