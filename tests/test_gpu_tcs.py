@@ -191,3 +191,32 @@ def test_f7_adam_curve_and_chunking(pe, golden):
     out2 = m2.train(2, 5e-4, 3)
     assert len(out2[4]) == 6
     np.testing.assert_allclose(out2[4], rec['loss'], rtol=1e-5)
+
+
+def test_engine_auto_and_env_default(pe, golden, monkeypatch):
+    """engine='auto' = tc3s for the collocation term (wide nets fall back to the SIMT engine per term); a constructor call with the
+    reference's own signature (no engine argument) reads $PE_ENGINE and stays on the SIMT engine when it is unset."""
+    g = golden('synthetic_5x50.npz')
+    layers = [3] + 5 * [50] + [5]
+    Ws, bs = R.xavier_params(layers, seed=1111)
+    outs = {}
+    for eng in ('tc3s', 'auto'):
+        m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=eng)
+        m.engine.evaluate()
+        assert m.engine.terms[0].engine == TCP
+        outs[eng] = m.engine.out.cpu().numpy().copy()
+    assert np.array_equal(outs['tc3s'], outs['auto'])
+    monkeypatch.setenv('PE_ENGINE', 'auto')
+    m = pe.PINN(g['f5_collo'], g['f5_hole'], None, None, None, None, None, None, layers, None, None, None, None, verbose=False)
+    m.uv_net.set_weights(Ws, bs)
+    m.engine.evaluate()
+    assert m.engine.terms[0].engine == TCP and np.array_equal(m.engine.out.cpu().numpy(), outs['auto'])
+    monkeypatch.delenv('PE_ENGINE')
+    m = pe.PINN(g['f5_collo'], g['f5_hole'], None, None, None, None, None, None, layers, None, None, None, None, verbose=False)
+    m.engine.build()
+    assert m.engine.terms[0].engine == 0
+    # hidden width 70 > 56: 'auto' keeps every term on the SIMT engine
+    wide = [3] + 3 * [70] + [5]
+    m = pe.PINN(g['f5_collo'][:256], g['f5_hole'][:32], None, None, None, None, None, None, wide, None, None, None, None, verbose=False, engine='auto')
+    m.engine.evaluate()
+    assert all(t.engine == 0 for t in m.engine.terms) and np.isfinite(m.engine.terms_host()).all()
