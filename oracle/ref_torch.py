@@ -6,11 +6,13 @@ torch.autograd (nested `torch.autograd.grad(..., create_graph=True)` standing in
 `pinn_elastodynamics_b200/` may import it.  Only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` use it.
 
-PARITY STATUS: "parity unpinned" by the reference itself -- the reference ships no tests, no
-golden loss/gradient vectors, and TensorFlow 1.x cannot be imported here.
-The oracle is pinned instead by (i) finite differences of its own loss, (ii) the shipped
-checkpoints: residual losses of the trained plate nets (loss_f_uv = 3.8686e-05,
-loss_f_s = 2.4435e-05 on the survey's 4,862-point set) and FEM rel-L2 bands, see
+PARITY STATUS: pinned to the reference's own source.  TensorFlow 1.x cannot be imported here and the reference ships no
+tests or golden loss/gradient vectors, so the four reference class files are executed unmodified on a
+TF1-primitive shim (oracle/tf1_shim.py) by tests/golden/make_reference_golden.py, and this oracle must reproduce their outputs
+(tests/golden/reference_tf1shim.npz; tests/test_reference_golden.py: terms / gradients 1e-10, Adam loops 1e-9, L-BFGS-B sequences
+1e-7).  Not covered: TensorFlow's own kernels -- the primitives' semantics come from TF's documentation.  Further pins:
+(i) finite differences of its own loss, (ii) the shipped checkpoints: residual losses of the trained plate nets
+(loss_f_uv = 3.8686e-05, loss_f_s = 2.4435e-05 on the survey's 4,862-point set) and FEM rel-L2 bands, see
 tests/test_oracle.py and tests/golden/make_golden.py.
 
 Reference files (relative to /root/reference):
