@@ -217,7 +217,37 @@ def wave(kind):
         OUT['semi_params_after_bfgs'] = flat_params(m)
 
 
+
+# ----------------------------------------------------------------------------------------------------------- host preprocessing helpers
+def helpers():
+    """the reference's own module-level point generators (pure numpy; plate:614-656,857-869, semi:397-409,633-657, conf:477-526,869-872)"""
+    P = tf.load_reference_module(REF + '/PlateHoleQuarter/train/train.py', 'ref_plate_h')
+    S = tf.load_reference_module(REF + '/ElasticWaveSemiInfinite/ElasticWave.py', 'ref_semi_h')
+    C = tf.load_reference_module(REF + '/ElasticWaveConfined/ElasticWave.py', 'ref_conf_h')
+    rng = np.random.default_rng(5)
+    x, y, t = P.GenDistPt(xmin=0, xmax=0.5, ymin=0, ymax=0.5, tmin=0, tmax=10, xc=0, yc=0, r=0.1, num_surf_pt=11, num=9, num_t=5)   # plate:921
+    XYT = np.concatenate((x, y, t), 1)
+    OUT['h_plate_GenDistPt'] = XYT
+    OUT['h_plate_GenDist'] = P.GenDist(XYT)
+    pts = rng.uniform([0, 0, 0], [.5, .5, 10], (500, 3))
+    OUT['h_pts_plate'] = pts
+    OUT['h_plate_DelHolePT'] = P.DelHolePT(pts, xc=0, yc=0, r=0.1)
+    OUT['h_plate_GenHoleSurfPT'] = np.concatenate(P.GenHoleSurfPT(xc=0, yc=0, r=0.1, N_PT=17), 1)
+    OUT['h_semi_CartGrid'] = np.concatenate(S.CartGrid(xmin=-15, xmax=15, ymin=-15, ymax=15, tmin=0, tmax=16, num=6, num_t=4), 1)
+    OUT['h_semi_GenCirclePT'] = np.concatenate(S.GenCirclePT(xc=0, yc=0, r=2.0, N_PT=23), 1)
+    ptw = rng.uniform([-15, -15, 0], [15, 15, 16], (500, 3))
+    ptw[:40, :2] = 2.0 * np.stack([np.cos(np.linspace(0, 6, 40)), np.sin(np.linspace(0, 6, 40))], 1)        # rows on / near the r = 2 circle
+    OUT['h_pts_wave'] = ptw
+    OUT['h_semi_DelSrcPT'] = S.DelSrcPT(ptw, xc=0, yc=0, r=2.0)          # keeps dst >= r (semi:657)
+    OUT['h_conf_DelSrcPT'] = C.DelSrcPT(ptw, xc=0, yc=0, r=2.0)          # keeps dst >  r (conf:872)
+    x, y, t = C.GenDistPt(xmin=-15, xmax=15, ymin=-15, ymax=15, tmin=0, tmax=14, xc=0, yc=0, r=2.0, num_surf_pt=13, num=8, num_t=4)
+    XYT = np.concatenate((x, y, t), 1)
+    OUT['h_conf_GenDistPt'] = XYT
+    OUT['h_conf_GenDist'] = C.GenDist(XYT)
+
+
 if __name__ == '__main__':
+    helpers()
     plate()
     for k in ('semi', 'inf', 'conf'):
         wave(k)

@@ -67,3 +67,22 @@ def test_fem_metrics():
     pred = [r * 1.01 for r in ref]
     m = P.fem_metrics(pred, ref, names=('u', 'v'))
     assert abs(m['u'] - 0.01) < 1e-12 and abs(m['v'] - 0.01) < 1e-12
+
+
+def test_helpers_match_the_reference_functions(golden):
+    """arrays returned by the reference's own module-level helpers (called in place from /root/reference by
+    tests/golden/make_reference_golden.py: plate:614-656,857-869; semi:397-409,633-657; conf:477-526,869-872)"""
+    G = golden('reference_tf1shim.npz')
+    cat = lambda cols: np.concatenate(cols, 1)
+    XYT = cat(P.GenDistPt(xmin=0, xmax=0.5, ymin=0, ymax=0.5, tmin=0, tmax=10, xc=0, yc=0, r=0.1, num_surf_pt=11, num=9, num_t=5))
+    np.testing.assert_array_equal(XYT, G['h_plate_GenDistPt'])
+    np.testing.assert_array_equal(P.GenDist(XYT), G['h_plate_GenDist'])
+    np.testing.assert_array_equal(P.DelHolePT(G['h_pts_plate'], xc=0, yc=0, r=0.1), G['h_plate_DelHolePT'])
+    np.testing.assert_array_equal(cat(P.GenHoleSurfPT(xc=0, yc=0, r=0.1, N_PT=17)), G['h_plate_GenHoleSurfPT'])
+    np.testing.assert_array_equal(cat(P.CartGrid(xmin=-15, xmax=15, ymin=-15, ymax=15, tmin=0, tmax=16, num=6, num_t=4)), G['h_semi_CartGrid'])
+    np.testing.assert_array_equal(cat(P.GenCirclePT(xc=0, yc=0, r=2.0, N_PT=23)), G['h_semi_GenCirclePT'])
+    np.testing.assert_array_equal(P.DelSrcPT(G['h_pts_wave'], 0, 0, 2.0), G['h_semi_DelSrcPT'])
+    np.testing.assert_array_equal(P.DelSrcPT(G['h_pts_wave'], 0, 0, 2.0, strict=True), G['h_conf_DelSrcPT'])
+    XYT = cat(P.GenDistPt(xmin=-15, xmax=15, ymin=-15, ymax=15, tmin=0, tmax=14, xc=0, yc=0, r=2.0, num_surf_pt=13, num=8, num_t=4, arc=2 * np.pi))
+    np.testing.assert_array_equal(XYT, G['h_conf_GenDistPt'])
+    np.testing.assert_allclose(P.GenDist_confined(XYT), G['h_conf_GenDist'], rtol=1e-15, atol=0)
