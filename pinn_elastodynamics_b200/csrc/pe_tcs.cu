@@ -13,15 +13,16 @@
 // layer l; when G0's activations are written, the issuer may already start G0 of layer l+1, and so on.  No extra TMEM or
 // shared memory: each group owns its accumulator columns, its activation operand planes and its bf16 "lo" operand columns.
 //
-// Roles (384 threads = 3 warpgroups; registers re-balanced with setmaxnreg: 200 per epilogue thread, 104 per control thread):
-//   warps 0..7   epilogue / converter warps: thread (p, h) owns TMEM lane p (a point) and the unit half h, as in pe_tc.cu
-//   warp 8       control warp: TMEM alloc/dealloc; lane 0 issues every tcgen05.mma / tcgen05.commit and the bulk-TMA copies
-//   warps 9..11  idle (they only complete the third warpgroup that setmaxnreg needs)
+// Roles (512 threads = 4 warpgroups; registers re-balanced with setmaxnreg: 136 per epilogue thread, 104 per control thread):
+//   warps 0..11  epilogue / converter warps: thread (p, h) owns TMEM lane p (a point) and the unit group h = warp / 4 (chunks 0-4, 5-9, 10-13)
+//   warp 12      control warp: TMEM alloc/dealloc; lane 0 issues every tcgen05.mma / tcgen05.commit and the bulk-TMA copies
+//   warps 13..15 idle (they only complete the fourth warpgroup that setmaxnreg needs)
+//   (TCS_EW = 8 builds the original 384-thread split: 8 epilogue warps with two unit halves, control warp 8)
 // Hand-shakes (mbarriers in shared memory, phase parities tracked per role):
-//   ACT[g]   (256 arrivals)  epilogue warps wrote group g's next operand (smem fp32 plane + TMEM lo columns)  -> issuer
+//   ACT[g]   (one arrival per epilogue thread)  epilogue warps wrote group g's next operand (smem fp32 plane + TMEM lo columns)  -> issuer
 //   ACC[g]   (tcgen05.commit) the MMAs of group g of the current layer are complete                          -> epilogue warps
 //   IMG[b]   (TMA complete_tx) weight operand image in buffer b has landed                                   -> issuer
-//   FULL[X] / EMPTY[X] / DW   the weight-gradient operand pipeline of pe_tcp.cu (now fed by all 8 converter warps)
+//   FULL[X] / EMPTY[X] / DW   the weight-gradient operand pipeline of pe_tcp.cu (now fed by all converter warps)
 // Weight operand images (36,864 B per matrix and direction, built per step by tcp_prep_kernel) are double buffered and
 // fetched with cp.async.bulk (1-D TMA) two layers ahead, instead of being staged through 36 registers per thread.
 // In the reverse sweep the weight-gradient phase needs both image buffers as scratch (bf16 hi/mid operand images), so the
@@ -38,7 +39,18 @@ namespace {
 using namespace pe_dev;
 using namespace pe_tcc;
 
-constexpr int S_THREADS = 384, S_EPI = 256;
+// TCS_EW = number of epilogue / converter warps: 12 (default: three unit groups of 5 / 5 / 4 chunks per TMEM lane quadrant, i.e. three
+// warps per scheduler for the latency-bound epilogues; 512-thread CTA, setmaxnreg 136 per epilogue thread / 104 per control thread --
+// the only split of the 64 K registers that leaves the issuer thread unspilled) or 8 (two unit halves of 7 chunks, 384 threads, 200 / 104).
+// Same arithmetic per element either way: bit-identical results.  Measured on B200 (profiles/r1_tc3s_ew12_ab.log): F5 0.3743 -> 0.3651
+// ms/step, F7 1.540 -> 1.510 ms/step with 12 warps.
+#ifndef TCS_EW
+#define TCS_EW 12
+#endif
+static_assert(TCS_EW == 8 || TCS_EW == 12, "TCS_EW: 8 or 12 epilogue warps");
+constexpr int S_EPI = 32 * TCS_EW, S_THREADS = S_EPI + 128;  // + the control warpgroup (issuer warp + three idle warps)
+constexpr int S_NH = TCS_EW / 4;                             // unit groups per lane quadrant
+constexpr int S_CTRL = TCS_EW;                               // index of the control warp
 constexpr int S_ACT = 0;
 constexpr int S_IMG0 = TC_MAX_STREAMS * TC_ACT_STREAM;       // 144,480: image buffer 0; weight-gradient phase: bf16 hi/mid images of A
 constexpr int S_IMG1 = S_IMG0 + TC_IMG_SET;                  // 181,344: image buffer 1; weight-gradient phase: bf16 hi/mid images of Zbar
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = lay.L;
     const int fast = args.fast;
-    const bool prof_on = PROF && args.prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 256);
+    const bool prof_on = PROF && args.prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == S_EPI);
     long long prof_t = 0;
     (void)prof_on; (void)prof_t;
     uint8_t* act = smem + S_ACT;
@@ -158,7 +170,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
         mbar_init(bar_dw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == S_CTRL) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -174,10 +186,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
     auto img_buf = [&](int i) { return (L + 1 - i) & 1; };
     auto img_src = [&](int i) { return (i <= L) ? args.images + (size_t)(i - 1) * TC_IMG_LAYER : args.images + (size_t)(L - 1) * TC_IMG_LAYER + TC_IMG_SET; };
 
-    if (warp >= 8) {
+    if (warp >= S_CTRL) {
         // ============================================================================================ control warpgroup
+#if TCS_EW == 8
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        if (warp == 8 && lane == 0) {
+#else
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+#endif
+        if (warp == S_CTRL && lane == 0) {
             uint32_t pact = 0, pimg = 0, pfull = 0;           // parity bits of the phases this thread waits for next
             uint32_t n_acc2 = 0, n_dw = 0;                   // commits issued so far on ACC[2] / DW (their completion parity = count & 1)
             auto load_img = [&](int i) {
@@ -271,12 +287,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
         __syncwarp();
     } else {
         // ============================================================================================ epilogue / converter warps
+#if TCS_EW == 8
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+#else
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+#endif
         const int p = 32 * (warp & 3) + lane;            // TMEM lane = point of the tile
-        const int h = warp >> 2;                         // unit half: chunks [7h, 7h+7)
+        const int h = warp >> 2;                         // unit group: chunks [c_lo, c_hi) = [7h, 7h+7) (two groups) or [5h, min(5h+5, 14)) (three)
+        const int c_lo = (S_NH == 2) ? 7 * h : 5 * h;
+        const int c_hi = (S_NH == 2) ? 7 * h + 7 : (h == 2 ? TC_NCH : 5 * h + 5);
         const uint32_t tlane = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
         // zero the bf16 "lo" operand columns once (units 56..63 are never written afterwards and must stay zero)
-        for (int c = h * 80; c < h * 80 + 80; c += 2) tm_st2(tlane + TM_LO + c, 0u, 0u);
+        for (int c = 2 * h; c < 160; c += 2 * S_NH) tm_st2(tlane + TM_LO + c, 0u, 0u);
         tm_wait_st();
         uint32_t pacc = 0, pempty = 0, pdw = 0;
         auto wait_acc = [&](int g) { mbar_wait(bar_acc + 8 * g, (pacc >> g) & 1u); pacc ^= 1u << g; };
@@ -299,7 +321,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 if (valid) { x = row[0]; y = row[1]; t = row[2]; }
                 *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(fmaf(x, Tc.in_scale[0], Tc.in_shift[0]), fmaf(y, Tc.in_scale[1], Tc.in_shift[1]),
                                                                         fmaf(t, Tc.in_scale[2], Tc.in_shift[2]), valid ? 1.f : 0.f);
-            } else {
+            } else if (h == 1) {
                 const int nt = tile + (int)gridDim.x;                      // pull this CTA's next tile towards L2
                 if (nt < ntiles) {
                     const bool nsec = nt >= ntiles_main;
@@ -321,7 +343,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 const int dout = lay.d[1];
                 float* st = stash;                                         // stash layer index 0 = outputs of layer 1
 #pragma unroll 1
-                for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float o[NS][4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -361,13 +383,13 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     __stcg(reinterpret_cast<float4*>(st + (size_t)k * (TC_STASH_STREAM / 4) + c * 512 + p * 4), v);
                     tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(v4[0], v4[1]), lo_pair(v4[2], v4[3]));
                 };
-                auto zero_pads = [&](int k) { if (h == 1) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); } };
+                auto zero_pads = [&](int k) { if (h == S_NH - 1) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); } };
                 // ---- G0: a = tanh(z_0 + b)
                 wait_acc(0);
                 TCS_PROF(1);
                 fence_after();
 #pragma unroll 1
-                for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float z[4];
                     tm_ld4(tlane + TM_ACC + 4 * c, z);
                     tm_wait_ld();
@@ -387,7 +409,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 TCS_PROF(3);
                 fence_after();
 #pragma unroll 1
-                for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     const float4 a4 = *reinterpret_cast<const float4*>(act + c * TC_CH + p * 16);
                     const float av[4] = {a4.x, a4.y, a4.z, a4.w};
                     float z1[4], z2[4];
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 TCS_PROF(5);
                 fence_after();
 #pragma unroll 1
-                for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     const float4 a4 = *reinterpret_cast<const float4*>(act + c * TC_CH + p * 16);
                     const float av[4] = {a4.x, a4.y, a4.z, a4.w};
                     float z3[4], z4[4];
@@ -523,8 +545,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                             *reinterpret_cast<uint4*>(smem + SW_AMID + c8 * 2048 + pp * 16) = mid;
                         }
                     }
-                    if (tid >= 192) {                        // chunk 7: units 56..63, unit 63 = ones row of the value stream (threads with one task)
-                        const int pp = 64 * X + (tid - 192);
+                    if (tid >= S_EPI - 64) {                 // chunk 7: units 56..63, unit 63 = ones row of the value stream (threads with one task)
+                        const int pp = 64 * X + (tid - (S_EPI - 64));
                         const uint32_t one_hi = (k == 0) ? 0x3F800000u : 0u;
                         *reinterpret_cast<uint4*>(smem + SW_AHI + 7 * 2048 + pp * 16) = make_uint4(0u, 0u, 0u, one_hi);
                         *reinterpret_cast<uint4*>(smem + SW_AMID + 7 * 2048 + pp * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -579,8 +601,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                     const int ldw = lay.ldw[m];
                     float* gW = gpart + lay.woff[m];
                     float* gB = gpart + lay.boff[m];
-                    const int c_lo = h ? 32 : 0, c_hi = h ? 56 : 32;
-                    for (int c = c_lo; c < c_hi; c += 8) {
+                    const int dr_lo = (S_NH == 2) ? (h ? 32 : 0) : (h == 0 ? 0 : (h == 1 ? 24 : 40));
+                    const int dr_hi = (S_NH == 2) ? (h ? 56 : 32) : (h == 0 ? 24 : (h == 1 ? 40 : 56));
+                    for (int c = dr_lo; c < dr_hi; c += 8) {
                         float v[8], v2[8];
                         tm_ld8(tlane + TM_LO + c, v);
                         tm_ld8(tlane + TM_LO + 56 + c, v2);          // the hm block
@@ -595,26 +618,26 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                             }
                         }
                     }
-                    if (h == 0) {   // the tile aliased lo-operand columns including zero pads (units 56..63): restore them
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
-                    }
                 }
-                // both unit halves (warps w and w + 4) share the TMEM lanes: the tile must be drained by both before either overwrites
-                // the aliased lo-operand columns below
+                // the unit groups (warps w, w + 4[, w + 8]) share the TMEM lanes: the tile must be drained by all of them before any of them
+                // overwrites the aliased lo-operand columns below
                 named_bar_sync(1, S_EPI);
+                if (h == 0) {   // the tile aliased lo-operand columns including zero pads (units 56..63): restore them
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
+                }
                 TCS_PROF(13);
                 // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs
                 float4 Anext[NS];
 #pragma unroll
-                for (int k = 0; k < NS; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (7 * h) * 512 + p * 4));
+                for (int k = 0; k < NS; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + c_lo * 512 + p * 4));
 #pragma unroll 1
-                for (int c = 7 * h; c < 7 * h + 7; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float ab[NS][4];
                     float4 Av[NS];
 #pragma unroll
                     for (int k = 0; k < NS; ++k) Av[k] = Anext[k];
-                    if (c + 1 < 7 * h + 7) {
+                    if (c + 1 < c_hi) {
 #pragma unroll
                         for (int k = 0; k < NS; ++k) Anext[k] = __ldcg(reinterpret_cast<const float4*>(stash_in + (size_t)k * (TC_STASH_STREAM / 4) + (c + 1) * 512 + p * 4));
                     }
@@ -645,7 +668,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                         tm_st2(tlane + TM_LO + 32 * k + 2 * c, lo_pair(v.x, v.y), lo_pair(v.z, v.w));
                     }
                 }
-                if (h == 1) {
+                if (h == S_NH - 1) {
 #pragma unroll
                     for (int k = 0; k < NS; ++k) { tm_st2(tlane + TM_LO + 32 * k + 28, 0u, 0u); tm_st2(tlane + TM_LO + 32 * k + 30, 0u, 0u); }
                 }
@@ -662,7 +685,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                 const int d1 = lay.d[1];
                 const int j = tid & 63, qq = tid >> 6;                    // 4 point quarters x 64 units
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f, gb = 0.f;
-                if (j < d1) {
+                if (j < d1 && tid < 256) {
                     const uint8_t* base = act + (j >> 2) * TC_CH + (j & 3) * 4;
 #pragma unroll 4
                     for (int s = 0; s < 32; ++s) {
@@ -678,7 +701,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
                         gb += zv;
                     }
                 }
-                *reinterpret_cast<float4*>(red + (qq * 64 + j) * 4) = make_float4(g0, g1, g2, gb);
+                if (tid < 256) *reinterpret_cast<float4*>(red + (qq * 64 + j) * 4) = make_float4(g0, g1, g2, gb);
                 named_bar_sync(1, S_EPI);
                 if (tid < 64 && tid < d1) {
                     float4 s = *reinterpret_cast<float4*>(red + tid * 4);
@@ -728,7 +751,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) resid_tcs_kernel(const TcsArgs a
     }
     fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+    if (warp == S_CTRL) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
 template <int NS, bool PROF>
