@@ -56,7 +56,7 @@ enum {
     PE_ENGINE_TCP_TF32X3 = 3,  /* second-generation tcgen05 engine (csrc/pe_tcp.cu): 3xTF32 split, weight-gradient phase as a
                                   converter-warps / MMA-warp pipeline; PE_RES_F5 (K=5) and PE_RES_F7 (K=4) */
     PE_ENGINE_TCP_TF32 = 4,    /* same, single-pass TF32 */
-    PE_ENGINE_TCS_TF32X3 = 5,  /* third-generation tcgen05 engine (csrc/pe_tcs.cu): warp-specialised (8 epilogue warps + MMA/TMA issuer
+    PE_ENGINE_TCS_TF32X3 = 5,  /* third-generation tcgen05 engine (csrc/pe_tcs.cu): warp-specialised (12 epilogue warps + MMA/TMA issuer
                                   warp), jet-stream groups pipelined through the forward pass, TMA-fed double-buffered weight images;
                                   same terms and networks as PE_ENGINE_TCP_* */
     PE_ENGINE_TCS_TF32 = 6     /* same, single-pass TF32 */
