@@ -217,12 +217,14 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import pinn_elastodynamics_b200 as pe
-    from oracle import ref_torch as R    # Xavier arrays only (identical to the reference-arm inputs); no oracle compute here
 
     n_total = args.points * world
     Collo, HOLE = make_workload(n_total)
     model = pe.PINN(Collo, HOLE, None, None, None, None, None, None, LAYERS, None, None, None, None, verbose=False, engine=args.engine)
-    Ws, bs = R.xavier_params(LAYERS, seed=1111)
+    # the package's own Xavier initialiser with the reference's seed: array-equal to the arrays the reference arm / cpu_baseline leg feed
+    # to the oracle (tests/test_host.py), so nothing under oracle/ is imported on this arm
+    from pinn_elastodynamics_b200.models import xavier_init_lists
+    Ws, bs = xavier_init_lists(LAYERS, np.random.default_rng(1111))
     model.uv_net.set_weights(Ws, bs)
     eng = model.engine
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')

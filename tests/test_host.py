@@ -143,3 +143,17 @@ def test_engine_support_matrix():
     assert lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3p']) == lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3']) == 148
     assert lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3p']) == lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3'])
     lib.pe_plan_destroy(plan)
+
+
+def test_bench_weights_equal_the_oracle_arm_weights():
+    """bench.py's GPU arm initialises with the package's own Xavier routine (nothing under oracle/ on that arm); the reference arm and
+    the cpu_baseline leg feed the oracle R.xavier_params(seed=1111): both must be the same arrays."""
+    from oracle import ref_torch as R
+    from pinn_elastodynamics_b200.models import xavier_init_lists
+    layers = [3] + 5 * [50] + [5]
+    a = R.xavier_params(layers, seed=1111)
+    b = xavier_init_lists(layers, np.random.default_rng(1111))
+    assert all(np.array_equal(x, y) for x, y in zip(a[0], b[0])) and all(np.array_equal(x, y) for x, y in zip(a[1], b[1]))
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py')).read()
+    main_arm = src[src.index('import pinn_elastodynamics_b200 as pe'):src.index("# ---- e2e")]
+    assert 'from oracle' not in main_arm and 'import oracle' not in main_arm
