@@ -26,6 +26,15 @@ def idesc(fmt, M, N, a_mn=0, b_mn=0):
     return (1 << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
 
 
+def idesc2(afmt, bfmt, M, N, a_mn=0, b_mn=0):
+    """separate A / B formats (kind::f16: 0 = F16, 1 = BF16); fp32 accumulate."""
+    return (1 << 4) | (afmt << 7) | (bfmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def f16_bits(x):
+    return np.asarray(x, np.float16).view(np.uint16)
+
+
 def sdesc(off, lbo, sbo, layout=0):
     return ((off >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16) | (((sbo >> 4) & 0x3FFF) << 32) | (1 << 46) | (layout << 61)
 
@@ -160,6 +169,38 @@ def t_bf16_ss(K=16, N=64):
     return np.array_equal(out, A @ B.T), out, A @ B.T
 
 
+def t_mixed_16bit_ss(afmt, bfmt, K=64, N=64):
+    """round-2 question (DESIGN 4.2c item 3): does kind::f16 accept A and B in DIFFERENT 16-bit formats (fp16 hi x bf16 lo split)?
+    Values are multiples of 1/8 in [-3, 3]: exact in both formats, and an fp16 pattern read as bf16 (or vice versa) gives garbage."""
+    rng = np.random.default_rng(9)
+    A = rng.integers(-24, 25, (128, K)).astype(np.float32) / 8
+    B = rng.integers(-24, 25, (N, K)).astype(np.float32) / 8
+    enc = lambda fmt, m: f16_bits(m) if fmt == 0 else bf16_bits(m)
+    ia, ib = chunked(enc(afmt, A), 8), chunked(enc(bfmt, B), 8)
+    smem = np.concatenate([ia.ravel().view(np.uint8), ib.ravel().view(np.uint8)])
+    offb = ia.size * 2
+    mm = [(1, sdesc(s * 2 * 128 * 16, 128 * 16, 128), sdesc(offb + s * 2 * N * 16, N * 16, 128), idesc2(afmt, bfmt, 128, N), 0, 1 if s else 0) for s in range(K // 16)]
+    out = run(smem, mm, N)
+    return np.array_equal(out, A @ B.T), out, A @ B.T
+
+
+def t_mixed_16bit_mn(afmt, bfmt, M=64, N=56, P=128):
+    """the weight-gradient shape (both operands MN-major, K = points) with fp16 A and bf16 Z or the other way round"""
+    rng = np.random.default_rng(10)
+    A = rng.integers(-24, 25, (P, M)).astype(np.float32) / 8
+    Z = rng.integers(-24, 25, (P, N)).astype(np.float32) / 8
+    enc = lambda fmt, m: f16_bits(m) if fmt == 0 else bf16_bits(m)
+    ia, iz = chunked(enc(afmt, A), 8), chunked(enc(bfmt, Z), 8)
+    smem = np.concatenate([ia.ravel().view(np.uint8), iz.ravel().view(np.uint8)])
+    offz = ia.size * 2
+    mm = [(1, sdesc(s * 256, 128, P * 16), sdesc(offz + s * 256, 128, P * 16), idesc2(afmt, bfmt, M, N, 1, 1), 0, 1 if s else 0) for s in range(P // 16)]
+    out = run(smem, mm, 64)
+    exp = A.T @ Z
+    lanes = np.concatenate([np.arange(16) + 32 * q for q in range(4)]) if M == 64 else np.arange(128)
+    got = out[lanes][:, :N]
+    return np.array_equal(got, exp), got, exp
+
+
 def t_bf16_ts(K=16, N=64, mixed=False):
     """A (bf16) from tensor memory, packed 2 per 32-bit column (element 2c in the low half); B bf16 K-major in smem."""
     rng = np.random.default_rng(4)
@@ -208,6 +249,10 @@ TESTS = [('kmajor tf32 K=8', lambda: t_kmajor_tf32()), ('kmajor tf32 K=8 swapped
          ('mnmajor bf16 M=64 N=56', lambda: t_mnmajor_bf16()), ('mnmajor bf16 swapped', lambda: t_mnmajor_bf16(swap=True)),
          ('mnmajor bf16 M=128 N=64', lambda: t_mnmajor_bf16(M=128, N=64)),
          ('cp 128x256b + tf32 TS', lambda: t_cp_and_tf32_ts(shape=4)), ('cp 128x128b + tf32 TS', lambda: t_cp_and_tf32_ts(shape=5)),
+         # round-2 hypotheses (not relied on yet): mixed 16-bit operand formats in one kind::f16 MMA
+         ('f16 x f16 SS K=64', lambda: t_mixed_16bit_ss(0, 0)), ('f16(A) x bf16(B) SS K=64', lambda: t_mixed_16bit_ss(0, 1)),
+         ('bf16(A) x f16(B) SS K=64', lambda: t_mixed_16bit_ss(1, 0)),
+         ('mnmajor f16(A) x bf16(Z) M=64 N=56', lambda: t_mixed_16bit_mn(0, 1)), ('mnmajor bf16(A) x f16(Z) M=64 N=56', lambda: t_mixed_16bit_mn(1, 0)),
          ('tf32 conversion', None)]
 
 
