@@ -223,6 +223,13 @@ void pe_debug_set_tc_profile(unsigned long long *d_counters16);
 void pe_debug_set_tcp_profile(unsigned long long *d_counters16);
 /* PE_ENGINE_TCS_*: d_counters32 = 32 device uint64: 0..15 phases of epilogue thread 0, 16..31 phases of the MMA/TMA issuer (CTA 0). */
 void pe_debug_set_tcs_profile(unsigned long long *d_counters32);
+/* EXPERIMENTAL (round-2 groundwork, csrc/pe_tc4_probe.cu; not used by any product path): forward jets d_out[n][K][O] like
+ * pe_forward_jets, computed on tensor cores with the fp16-hi + bf16-lo operand split (mixed-format kind::f16 MMAs, one accumulator).
+ * K = 4 or 5, hidden widths <= 56, <= 8 outputs.  d_scratch: pe_debug_tc4_scratch_bytes(plan) bytes.  variant bit 0: 1 = 7-chunk operand
+ * planes with LBO = 0 on the last K-step, 0 = 8-chunk planes with a zero pad chunk. */
+size_t pe_debug_tc4_scratch_bytes(const pe_plan *plan);
+int pe_debug_forward_jets_tc4(const pe_plan *plan, int K, const float *d_points, int ld, int n, const float *in_scale, const float *in_shift,
+                              const float *d_params, void *d_scratch, float *d_out, int variant, void *stream);
 /* PE_ENGINE_TCP_*: 1 (default) = pipelined weight-gradient phase, 0 = the serial phase order of PE_ENGINE_TC_* (A/B timing). */
 void pe_debug_set_tcp_pipeline(int on);
 

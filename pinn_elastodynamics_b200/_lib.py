@@ -83,6 +83,8 @@ SYMBOLS = [
     ('pe_debug_set_tcp_profile', None, [_vp]),
     ('pe_debug_set_tcp_pipeline', None, [_i]),
     ('pe_debug_set_tcs_profile', None, [_vp]),
+    ('pe_debug_tc4_scratch_bytes', C.c_size_t, [_vp]),
+    ('pe_debug_forward_jets_tc4', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp, _i, _vp]),
 ]
 
 _lib = None
