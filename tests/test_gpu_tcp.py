@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import ref_torch as R
-from tests.util import layers_of, per_layer_grad_err, random_biases, rel_err, unpack_golden
+from tests.util import per_layer_grad_err, random_biases, rel_err, unpack_golden
 from tests.test_gpu_parity import _check, _plate, _wave_sets
 
 pytestmark = pytest.mark.gpu

@@ -1,8 +1,6 @@
 """Helpers shared by the GPU parity tests (oracle = checker only)."""
 import numpy as np
 
-from oracle import ref_torch as R
-
 
 def unpack_golden(g, prefix):
     Ws, bs, i = [], [], 0
