@@ -1,7 +1,8 @@
 """OPT-IN (PE_TEST_TC4=1): forward-only probe of the next tensor-core engine's arithmetic (csrc/pe_tc4_probe.cu) against
 the SIMT fp32 forward jets.  The probe was written after round 1's GPU budget was spent and has not run on hardware yet, so it is not
 part of the default `-m gpu` suite; round 2 starts with   PE_TEST_TC4=1 python -m pytest tests/test_gpu_tc4_forward.py -q   .
-Expected (CPU model, tests/emulate_engine_precision.py): ~1e-6 of each stream's output scale per layer GEMM."""
+Expected from the CPU model of the arithmetic (tests/emulate_engine_precision.py): ~2e-6 of each stream's output scale after five layers
+(the shipped TF32 split: ~5e-6); the bar below is 1e-5."""
 import ctypes as C
 import os
 
@@ -47,16 +48,16 @@ def test_forward_jets_on_the_16_bit_split(K, O, variant):
     got, ref = _run([3] + 5 * [50] + [O], K, 1000, variant)
     assert np.isfinite(got).all()
     for k in range(K):      # per stream: error against that stream's output scale
-        assert np.abs(got[:, k] - ref[:, k]).max() <= 2e-5 * max(1e-30, np.abs(ref[:, k]).max()), (k, np.abs(got[:, k] - ref[:, k]).max(), np.abs(ref[:, k]).max())
+        assert np.abs(got[:, k] - ref[:, k]).max() <= 1e-5 * max(1e-30, np.abs(ref[:, k]).max()), (k, np.abs(got[:, k] - ref[:, k]).max(), np.abs(ref[:, k]).max())
 
 
 @pytest.mark.parametrize('n', [1, 127, 129, 128 * 149 + 3])
 def test_ragged_point_counts_and_narrow_nets(n):
     got, ref = _run([3, 14, 30, 5], 5, n, 1)
-    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
 def test_normalised_inputs():
     lb, ub = np.array([0., 0, 0]), np.array([30., 30, 20.])
     got, ref = _run([3] + 3 * [50] + [7], 4, 500, 1, lb, ub)
-    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
