@@ -59,7 +59,10 @@ enum {
     PE_ENGINE_TCS_TF32X3 = 5,  /* third-generation tcgen05 engine (csrc/pe_tcs.cu): warp-specialised (12 epilogue warps + MMA/TMA issuer
                                   warp), jet-stream groups pipelined through the forward pass, TMA-fed double-buffered weight images;
                                   same terms and networks as PE_ENGINE_TCP_* */
-    PE_ENGINE_TCS_TF32 = 6     /* same, single-pass TF32 */
+    PE_ENGINE_TCS_TF32 = 6,    /* same, single-pass TF32 */
+    PE_ENGINE_TC4 = 7          /* EXPERIMENTAL fourth-generation tcgen05 engine (csrc/pe_tc4.cu): one fp16-hi + bf16-lo operand split
+                                  for forward, adjoint and weight-gradient GEMMs, TMA-fed weight gradient without a conversion pass; written at
+                                  the end of round 1, not yet validated on hardware; opt-in only (never chosen by 'auto') */
 };
 
 typedef struct pe_plan pe_plan; /* host-side description of one network: dims, padded layout, launch config */
