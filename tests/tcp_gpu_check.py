@@ -63,8 +63,8 @@ def f5(flush):
     Collo, HOLE = bench.make_workload(50000)
     Ws, bs = R.xavier_params(layers, seed=1111)
     ref = {}
-    for name, eng_name, pipe in (('simt', 'simt', 1), ('tc3', 'tc3', 1), ('tc3p_serial', 'tc3p', 0), ('tc3p_pipe', 'tc3p', 1), ('tc3s', 'tc3s', 1)):
-        if ONLY and name not in ONLY and name not in ('simt', 'tc3'):
+    for name, eng_name, pipe in (('simt', 'simt', 1), ('tc3', 'tc3', 1), ('tc3p_serial', 'tc3p', 0), ('tc3p_pipe', 'tc3p', 1), ('tc3s', 'tc3s', 1), ('tc4', 'tc4', 1)):
+        if (ONLY and name not in ONLY and name not in ('simt', 'tc3')) or (name == 'tc4' and 'tc4' not in ONLY):
             continue
         lib.pe_debug_set_tcp_pipeline(pipe)
         m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine=eng_name)
@@ -76,7 +76,7 @@ def f5(flush):
         row = dict(case='f5', engine=name, terms=[float(x) for x in t])
         if name != 'simt':
             row['terms_rel_vs_simt'] = rel(t, ref['simt'][0]); row['grad_rel_vs_simt'] = rel(g, ref['simt'][1])
-        if name.startswith('tc3p') or name == 'tc3s':
+        if name.startswith('tc3p') or name in ('tc3s', 'tc4'):
             row['grad_rel_vs_tc3'] = rel(g, ref['tc3'][1]); row['bit_equal_tc3'] = bool(np.array_equal(g, ref['tc3'][1]))
         emit(**row)
         if name != 'simt':
@@ -98,8 +98,8 @@ def f7(flush):
     layers = [3] + 5 * [50] + [7]
     Ws, bs = R.xavier_params(layers, seed=1111); Ws[0] = Ws[0] * 0.1
     ref = {}
-    for name, eng_name, pipe in (('simt', 'simt', 1), ('tc3p_serial', 'tc3p', 0), ('tc3p_pipe', 'tc3p', 1), ('tc3s', 'tc3s', 1)):
-        if ONLY and name not in ONLY and name != 'simt':
+    for name, eng_name, pipe in (('simt', 'simt', 1), ('tc3p_serial', 'tc3p', 0), ('tc3p_pipe', 'tc3p', 1), ('tc3s', 'tc3s', 1), ('tc4', 'tc4', 1)):
+        if (ONLY and name not in ONLY and name != 'simt') or (name == 'tc4' and 'tc4' not in ONLY):
             continue
         lib.pe_debug_set_tcp_pipeline(pipe)
         m = pe.DeepHPM(P, SRC, IC, UP, layers, lb, ub, verbose=False, engine=eng_name)
