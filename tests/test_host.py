@@ -137,6 +137,10 @@ def test_engine_support_matrix():
     assert sup([3, 56, 56, 5], L.RES_F5, 5, 'tc3p') == 1 and sup([3, 57, 56, 5], L.RES_F5, 5, 'tc3p') == 0
     assert sup([3, 50, 5], L.RES_F5, 5, 'tc3p') == 1                                # one hidden layer: FFMA first layer + tensor-core output layer
     assert sup(f5, L.RES_F7, 4, 'tc3p') == 0 and sup(f7, L.RES_F5, 5, 'tc3p') == 0   # K / output count must match the formulation
+    # 'auto' is the validated warp-specialised engine; the experimental fourth generation is opt-in and needs two hidden layers
+    assert L.ENGINES['auto'] == L.ENGINES['tc3s'] != L.ENGINES['tc4']
+    assert sup(f5, L.RES_F5, 5, 'tc4') == 1 and sup(f7, L.RES_F7, 4, 'tc4') == 1 and sup([3, 50, 5], L.RES_F5, 5, 'tc4') == 0
+    assert sup(f5, L.RES_TRACTION, 1, 'tc4') == 0 and sup(w100, L.RES_F7, 4, 'tc4') == 0
     # slots / scratch queries are engine-aware
     dims = (C.c_int * len(f5))(*f5)
     plan = lib.pe_plan_create(dims, len(f5), -1)
