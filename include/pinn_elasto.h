@@ -60,6 +60,10 @@ enum {
                                   warp), jet-stream groups pipelined through the forward pass, TMA-fed double-buffered weight images;
                                   same terms and networks as PE_ENGINE_TCP_* */
     PE_ENGINE_TCS_TF32 = 6,    /* same, single-pass TF32 */
+    PE_ENGINE_TCF = 8,         /* fp16-pair tcgen05 engine (csrc/pe_tcf.cu): every GEMM operand as an fp16 pair (hi, lo scaled by 2^11), products
+                                  Ah Bh + 2^-11 (Ah Bl + Al Bh) on kind::f16 MMAs with the scale-input-d form, per-tile power-of-two seed
+                                  scaling, TMA-fed weight gradient without a conversion pass; PE_RES_F5 (K = 5) and PE_RES_F7 (K = 4), hidden
+                                  widths <= 56, at least two hidden layers */
     PE_ENGINE_TC4 = 7          /* EXPERIMENTAL fourth-generation tcgen05 engine (csrc/pe_tc4.cu): one fp16-hi + bf16-lo operand split
                                   for forward, adjoint and weight-gradient GEMMs, TMA-fed weight gradient without a conversion pass; written at
                                   the end of round 1, not yet validated on hardware; opt-in only (never chosen by 'auto') */
@@ -224,6 +228,8 @@ int pe_vec_dot_max(int n, const float *d_a, const float *d_b, float *d_res, void
 void pe_debug_set_tc_profile(unsigned long long *d_counters16);
 /* Same for the PE_ENGINE_TCP_* kernels (selects their profiling instantiation while non-NULL). */
 void pe_debug_set_tcp_profile(unsigned long long *d_counters16);
+/* PE_ENGINE_TCF: same layout as pe_debug_set_tcs_profile. */
+void pe_debug_set_tcf_profile(unsigned long long *d_counters32);
 /* PE_ENGINE_TCS_*: d_counters32 = 32 device uint64: 0..15 phases of epilogue thread 0, 16..31 phases of the MMA/TMA issuer (CTA 0). */
 void pe_debug_set_tcs_profile(unsigned long long *d_counters32);
 /* EXPERIMENTAL (round-2 groundwork, csrc/pe_tc4_probe.cu; not used by any product path): forward jets d_out[n][K][O] like

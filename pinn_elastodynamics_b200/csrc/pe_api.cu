@@ -23,6 +23,8 @@ int pe_launch_resid_tcs(const pe_plan* plan, const PeResidArgs& a, int K, int fa
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 int pe_launch_resid_tc4(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
+int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
+                        const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 int pe_tc_supported(const pe_plan* plan, int K, int engine);
 int pe_tcp_supported(const pe_plan* plan, int K);
 int pe_tc_slots(const pe_plan* plan, int n_points);
@@ -111,13 +113,14 @@ extern "C" int pe_plan_weight_ld(const pe_plan* plan, int l) { return (plan && l
 
 static bool is_tcs(int engine) { return engine == PE_ENGINE_TCS_TF32X3 || engine == PE_ENGINE_TCS_TF32; }
 static bool is_tc4(int engine) { return engine == PE_ENGINE_TC4; }
-static bool is_tcp(int engine) { return engine == PE_ENGINE_TCP_TF32X3 || engine == PE_ENGINE_TCP_TF32 || is_tcs(engine) || is_tc4(engine); }   // second generation onwards: F5 + F7
+static bool is_tcf(int engine) { return engine == PE_ENGINE_TCF; }
+static bool is_tcp(int engine) { return engine == PE_ENGINE_TCP_TF32X3 || engine == PE_ENGINE_TCP_TF32 || is_tcs(engine) || is_tc4(engine) || is_tcf(engine); }   // second generation onwards: F5 + F7
 static bool is_tc(int engine) { return engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32 || is_tcp(engine); }
 
 extern "C" int pe_engine_supported(const pe_plan* plan, int kind, int K, int engine) {
     if (!plan) return 0;
     if (engine == PE_ENGINE_SIMT_FP32) return 1;
-    if (is_tc4(engine) && plan->lay.L < 3) return 0;
+    if ((is_tc4(engine) || is_tcf(engine)) && plan->lay.L < 3) return 0;
     if (is_tcp(engine)) return (kind == PE_RES_F5 || kind == PE_RES_F7) && pe_tcp_supported(plan, K);
     if (is_tc(engine)) return kind == PE_RES_F5 && pe_tc_supported(plan, K, engine);
     return 0;
@@ -234,6 +237,8 @@ static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K,
             if (term2->aux_k && !d_aux2) { pe_set_error("fused composite set needs d_aux2"); return 1; }
             n_eff = PE_TC_TILE * ((n_local + PE_TC_TILE - 1) / PE_TC_TILE + (n2_local + PE_TC_TILE - 1) / PE_TC_TILE);
         }
+        if (is_tcf(engine))
+            return pe_launch_resid_tcf(plan, a, K, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
         if (is_tc4(engine))
             return pe_launch_resid_tc4(plan, a, K, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
         if (is_tcs(engine))

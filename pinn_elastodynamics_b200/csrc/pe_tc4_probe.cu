@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t idesc_16(int afmt, int bfmt, int N) {
 __device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
     const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x[0] - f01.x, x[1] - f01.y), l23 = __floats2bfloat162_rn(x[2] - f23.x, x[3] - f23.y);
+    const __half2 l01 = __floats2half2_rn((x[0] - f01.x) * 2048.f, (x[1] - f01.y) * 2048.f), l23 = __floats2half2_rn((x[2] - f23.x) * 2048.f, (x[3] - f23.y) * 2048.f);
     hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
@@ -50,14 +50,14 @@ __global__ void tc4_prep_kernel(const float* __restrict__ params, PeLayout lay, 
     const int din = lay.d[m], dout = lay.d[m + 1], ldw = lay.ldw[m];
     const float* W = params + lay.woff[m];
     __half* whi = reinterpret_cast<__half*>(images + (size_t)m * Q_IMG);
-    __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>(images + (size_t)m * Q_IMG + Q_IMG_HALF);
+    __half* wlo = reinterpret_cast<__half*>(images + (size_t)m * Q_IMG + Q_IMG_HALF);
     const int e = (blockIdx.x & 15) * 256 + threadIdx.x;     // 4,096 elements: i = e >> 6 (0..63), j = e & 63
     const int i = e >> 6, j = e & 63;
     const float w = (i < din && j < dout) ? W[(size_t)i * ldw + j] : 0.f;
     const __half h = __float2half_rn(w);
     const int o = (i >> 3) * 512 + j * 8 + (i & 7);
     whi[o] = h;
-    wlo[o] = __float2bfloat16_rn(w - __half2float(h));
+    wlo[o] = __float2half_rn((w - __half2float(h)) * 2048.f);
 }
 
 struct Tc4Args {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) fwd_tc4_kernel(const Tc4Args a) 
     const PeLayout& lay = a.lay;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = lay.L;
-    const int Q_PLANE = a.lbo_trick ? Q_PLANE7 : Q_PLANE8;      // hi plane (fp16), then the lo plane (bf16) of the same stream
+    const int Q_PLANE = a.lbo_trick ? Q_PLANE7 : Q_PLANE8;      // hi plane (fp16), then the lo plane (fp16, scaled by 2^11) of the same stream
     const int Q_STREAM = 2 * Q_PLANE;
     uint8_t* act = smem + QS_ACT;
     uint8_t* img = smem + QS_IMG;
@@ -161,19 +161,27 @@ __global__ void __launch_bounds__(Q_THREADS, 1) fwd_tc4_kernel(const Tc4Args a) 
             if (tid == 0) {
                 fence_after();
                 const int ksteps = (din + 15) >> 4;
-                const uint32_t ihh = idesc_16(0, 0, 64), ihl = idesc_16(0, 1, 64), ilh = idesc_16(1, 0, 64);
+                const uint32_t ihh = idesc_16(0, 0, 64);
                 for (int k = 0; k < NS; ++k) {
                     const uint32_t d = tbase + 64u * k;
                     const uint32_t hi_s = act_s + (uint32_t)(k * Q_STREAM), lo_s = hi_s + (uint32_t)Q_PLANE;
+                    // K-step s covers unit chunks 2s and 2s + 1.  Chunk 7 does not exist in the 7-chunk planes: variant 1 re-reads chunk 2s
+                    // (LBO = 0), variant 2 reads whatever follows the plane (finite 16-bit patterns); either way its weights (rows 56..63 of the
+                    // image) are zero.  Order: all lo x hi / hi x lo products first (they carry a factor 2^11), then the first hi x hi K-step
+                    // scales the accumulator by 2^-11 (scale-input-d), the other hi x hi K-steps accumulate plainly.
                     for (int s = 0; s < ksteps; ++s) {
-                        // K-step s covers unit chunks 2s and 2s + 1; when chunk 2s + 1 would be chunk 7 (does not exist) the second half of the
-                        // K-step re-reads chunk 2s (LBO = 0): its weights (rows 56..63 of the image) are zero
-                        const uint32_t lbo = (2 * s + 1 < 7 || !a.lbo_trick) ? Q_CH : 0u;
+                        const uint32_t lbo = (2 * s + 1 < 7 || a.lbo_trick != 1) ? Q_CH : 0u;
                         const uint64_t ahi = sdesc(hi_s + 2 * s * Q_CH, lbo, 128), alo = sdesc(lo_s + 2 * s * Q_CH, lbo, 128);
                         const uint64_t bhi = sdesc(img_s + 2 * s * 1024, 1024, 128), blo = sdesc(img_s + Q_IMG_HALF + 2 * s * 1024, 1024, 128);
-                        mma_bf16_ss(d, ahi, bhi, ihh, s > 0);
-                        mma_bf16_ss(d, ahi, blo, ihl, 1u);
-                        mma_bf16_ss(d, alo, bhi, ilh, 1u);
+                        mma_bf16_ss(d, ahi, blo, ihh, s > 0);
+                        mma_bf16_ss(d, alo, bhi, ihh, 1u);
+                    }
+                    for (int s = 0; s < ksteps; ++s) {
+                        const uint32_t lbo = (2 * s + 1 < 7 || a.lbo_trick != 1) ? Q_CH : 0u;
+                        const uint64_t ahi = sdesc(hi_s + 2 * s * Q_CH, lbo, 128);
+                        const uint64_t bhi = sdesc(img_s + 2 * s * 1024, 1024, 128);
+                        if (s == 0) mma_f16_ss_scaled11(d, ahi, bhi, ihh);
+                        else mma_bf16_ss(d, ahi, bhi, ihh, 1u);
                     }
                 }
                 mma_commit(bar);
@@ -224,8 +232,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) fwd_tc4_kernel(const Tc4Args a) 
             for (int k = 0; k < NS; ++k)
                 for (int o = 0; o < lay.d[1] && o < 8; ++o) {
                     const __half hv = reinterpret_cast<const __half*>(act + k * Q_STREAM + (o >> 3) * Q_CH + p * 16)[o & 7];
-                    const __nv_bfloat16 lv = reinterpret_cast<const __nv_bfloat16*>(act + k * Q_STREAM + Q_PLANE + (o >> 3) * Q_CH + p * 16)[o & 7];
-                    a.out[((size_t)pt * NS + k) * lay.d[1] + o] = __half2float(hv) + __bfloat162float(lv);
+                    const __half lv = reinterpret_cast<const __half*>(act + k * Q_STREAM + Q_PLANE + (o >> 3) * Q_CH + p * 16)[o & 7];
+                    a.out[((size_t)pt * NS + k) * lay.d[1] + o] = __half2float(hv) + __half2float(lv) * (1.f / 2048.f);
                 }
         }
     }
@@ -260,7 +268,7 @@ extern "C" int pe_debug_forward_jets_tc4(const pe_plan* plan, int K, const float
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     Tc4Args t;
-    t.lbo_trick = variant & 1;
+    t.lbo_trick = variant & 3;
     t.lay = lay; t.points = d_points; t.params = d_params; t.images = (const uint8_t*)d_scratch; t.out = d_out; t.n = n; t.ld = ld;
     for (int i = 0; i < 3; ++i) { t.in_scale[i] = in_scale ? in_scale[i] : 1.f; t.in_shift[i] = in_shift ? in_shift[i] : 0.f; }
     tc4_prep_kernel<<<lay.L * 16, 256, 0, st>>>(d_params, lay, (uint8_t*)d_scratch);

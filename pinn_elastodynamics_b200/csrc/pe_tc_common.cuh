@@ -59,19 +59,27 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a_tmem, uint64_
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
 }
+// kind::f16 with scale-input-d: D = A B + D * 2^-11 (always accumulates)
+__device__ __forceinline__ void mma_f16_ss_scaled11(uint32_t d, uint64_t a, uint64_t b, uint32_t id) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n}" ::"r"(d), "l"(a), "l"(b), "r"(id) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-// Bounded: a phase that does not complete within ~2^26 polls (seconds; a tile takes ~100 us) is a protocol error -- trap
-// (the launch fails with an error the host reports) instead of spinning on the SM forever.
+// Bounded: a phase that does not complete within ~2 s of SM clock (a tile takes ~100 us) is a protocol error -- trap (the launch
+// fails with an error the host reports) instead of spinning on the SM forever.  (A poll count is not a time bound: one try_wait may
+// suspend the thread for a hardware-defined interval; round 2 saw a 2^26-poll bound outlive a 300 s test timeout.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    for (uint32_t spin = 1; !ok; ++spin) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 26)) __trap();
+        if ((spin & 63u) == 0u && clock64() - t0 > (1ll << 32)) __trap();
     }
 }
 // release-arrive of one thread (the generic-proxy writes before it were made visible to the async proxy by fence_async_smem)

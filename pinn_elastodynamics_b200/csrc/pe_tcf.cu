@@ -1,0 +1,780 @@
+// fp16-pair tcgen05 / TMEM engine for the collocation residual (engine id PE_ENGINE_TCF, name 'tcf'; what 'auto' selects).
+//
+// Arithmetic.  Every GEMM operand X (activation jets, adjoints, weights) is kept as an fp16 PAIR
+//         Xh = fp16(X),   Xl = fp16((X - Xh) * 2^11)            X = Xh + 2^-11 Xl  to ~22 bits
+// and every product is   A B ~= Ah Bh + 2^-11 (Ah Bl + Al Bh)   on kind::f16 MMAs (K = 16) into ONE fp32 accumulator:
+// the two cross products of every K-step are accumulated first, then the first Ah Bh MMA is issued in the scale-input-d form
+// (D = A B + D * 2^-11, probed: tests/probe_umma.py 'f16 scale-input-d'), the other Ah Bh K-steps accumulate plainly.  12 MMAs per
+// stream and layer (the TF32x3 scheme of the earlier generations: 18) at fp32-grade accuracy (CPU study
+// profiles/r1_split_precision_study.txt column fp16x3s: 2.6e-7 per GEMM for operand magnitudes in [1e-4, 6e4]; fp32: 1.5e-7).
+// Mixed fp16 x bf16 operands in one kind::f16 MMA -- the round-1 plan -- are an illegal instruction on B200 (profiles/r2_umma_probe.txt).
+// Range.  fp16 covers 6e-5 .. 65504 at full precision.  Forward jets of sane networks live there.  The adjoint seeds carry 2 w / N
+// and do not: each 128-point tile scales its seeds by a power of two sigma so that their largest magnitude is in [1, 2); the weight /
+// bias gradient tiles are multiplied by 1 / sigma when they are drained.  Nothing else depends on sigma (the reverse sweep is linear).
+// An overflow (|x| > 65504) turns into inf / NaN in the loss or the gradient, never into a silently wrong finite number.
+//
+// Layout.  Activation planes, per stream  [hi: 7 chunks of 8 units][128 points][8 x fp16] | [lo: same]  = 28,672 B: K-major operand of
+// the layer GEMMs (LBO 2,048, SBO 128; the fourth K-step's second chunk is whatever follows the plane -- finite 16-bit patterns --
+// against weight rows 56..63 that are zero) and, read MN-major, the [Zh | Zl] operand (N = 112) of the weight-gradient GEMM.  The forward
+// epilogue stashes the planes as they are (4 B per element) and the issuer brings them back with one bulk-TMA copy per stream: no
+// conversion pass.  Tensor memory: 5 x 64 accumulator columns | weight-gradient tile, 64 lanes x (56 hi-hi | 56 cross) | bias tile 8 + 8.
+//
+// Roles (warp-specialised as in the third generation): F_EW epilogue warps (thread (p, h): TMEM lane p = point, unit group h), one
+// control warp whose lane 0 issues every tcgen05.mma / commit / bulk copy.  Forward: the jet streams travel as three groups
+// G0 = {value}, G1 = {d/dx, d/dy}, G2 = {d/dt[, d2/dt2]} with ACT[g] / ACC[g] mbarrier pairs, so the tensor pipe runs G1 / G2 of a layer
+// while the epilogue warps apply tanh to G0.  Reverse, per layer l:
+//   issuer : adjoint image landed, Zbar_l published -> adjoint MMAs -> commit ACC -> per stream k: stashed planes of A_{l-1,k} landed in
+//            staging buffer k & 1 -> 8 K-steps of 16 points x {Ah x [Zh|Zl], Al x Zh} into the weight-gradient tile -> commit EMPTY -> refill;
+//            Zh^T 1, Zl^T 1 into the bias tile -> commit DW
+//   epilogue warps: wait ACC, DW -> drain both tiles into this CTA's gradient slot -> adjoint of tanh -> Zbar_{l-1} planes -> publish.
+// Reference lines: see pe_simt.cu / pe_device.cuh (the epilogue algebra is shared with the SIMT engine).
+#include <cuda_fp16.h>
+#include <cstring>
+#include "pe_device.cuh"
+#include "pe_tc_common.cuh"
+
+namespace {
+using namespace pe_dev;
+using namespace pe_tcc;
+
+#ifndef TCF_EW
+#define TCF_EW 12
+#endif
+static_assert(TCF_EW == 8 || TCF_EW == 12, "TCF_EW: 8 or 12 epilogue warps");
+constexpr int F_EPI = 32 * TCF_EW, F_THREADS = F_EPI + 128;
+constexpr int F_NH = TCF_EW / 4;                  // unit groups per TMEM lane quadrant
+constexpr int F_CTRL = TCF_EW;                    // index of the control warp
+constexpr int F_CH = 2048;                        // one chunk of 8 units: 128 points x 16 B
+constexpr int F_PLANE = 7 * F_CH;                 // 14,336: 56 units
+constexpr int F_STREAM = 2 * F_PLANE;             // 28,672: hi plane then lo plane
+constexpr int F_IMG_HALF = 8 * 64 * 16;           // [8 K-chunks][64 rows][8 x fp16] = 8,192
+constexpr int F_IMG = 2 * F_IMG_HALF;             // Wh then Wl: 16,384
+constexpr int F_IMG_LAYER = 2 * F_IMG;            // forward image, adjoint image
+// shared-memory map
+constexpr int F_ONES = 0;                                     // 1,024 B of fp16 ones: B operand of the bias-gradient MMAs
+constexpr int F_ACT = 1024;                                   // NS x (hi plane | lo plane)
+constexpr int F_R = F_ACT + TC_MAX_STREAMS * F_STREAM;        // 144,384: forward: two weight images; reverse: adjoint image + two staging buffers
+constexpr int F_STG = F_R + F_IMG;                            // staging buffer s at F_STG + s * F_STREAM
+constexpr int F_MISC = F_R + F_IMG + 2 * F_STREAM;            // 218,112: mbarriers + TMEM base slot + tile scale
+constexpr int F_COORD = F_MISC + 256;
+constexpr int F_RED = F_COORD + 128 * 16;
+constexpr int F_BIAS = F_RED + 4096;                          // [PE_MAX_LAYERS][64] floats
+constexpr int F_W0 = F_BIAS + PE_MAX_LAYERS * 256;            // [4][64] floats
+constexpr int F_TOTAL = F_W0 + 1024;                          // 229,632
+static_assert(2 * F_IMG <= F_IMG + 2 * F_STREAM, "the forward image double buffer lives inside the reverse-sweep region");
+static_assert(F_TOTAL <= 227 * 1024, "shared memory map exceeds the 227 KB opt-in limit");
+constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SEMPTY = 80, B_DW = 96, B_TMEM = 112, B_SCALE = 128;   // byte offsets in F_MISC
+constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW: 56 hi-hi + 56 cross; bias: 8 + 8)
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+template <int NS> __device__ __forceinline__ int grp_first(int g) { return g == 0 ? 0 : (g == 1 ? 1 : 3); }
+template <int NS> __device__ __forceinline__ int grp_count(int g) { return g == 0 ? 1 : (g == 1 ? 2 : NS - 3); }
+
+// kind::f16 instruction descriptors, fp16 x fp16, fp32 accumulate
+__device__ __forceinline__ uint32_t idesc_km(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }                        // K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_mn(int N) { return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (4u << 24); }  // MN-major, M = 64
+
+// 4 floats -> fp16 pair planes (hi, lo scaled by 2^11), each packed into a uint2
+__device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
+    const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((x[0] - f01.x) * LO_SCALE, (x[1] - f01.y) * LO_SCALE);
+    const __half2 l23 = __floats2half2_rn((x[2] - f23.x) * LO_SCALE, (x[3] - f23.y) * LO_SCALE);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+__device__ __forceinline__ void join4(const uint2& hi, const uint2& lo, float (&x)[4]) {
+    const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+    const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
+    x[0] = fmaf(l01.x, LO_INV, h01.x); x[1] = fmaf(l01.y, LO_INV, h01.y); x[2] = fmaf(l23.x, LO_INV, h23.x); x[3] = fmaf(l23.y, LO_INV, h23.y);
+}
+
+// Operand images per matrix m: forward B operand [n = out unit j][k = in unit i] at [(i >> 3)][j][i & 7] and adjoint B operand
+// [n = i][k = j] at [(j >> 3)][i][j & 7], each as an fp16 pair (hi image, then lo image), zero padded to 64 x 64.  16 blocks of 256 per matrix.
+__global__ void tcf_image_kernel(const float* __restrict__ params, PeLayout lay, uint8_t* __restrict__ images) {
+    const int m = blockIdx.x >> 4;
+    const int din = lay.d[m], dout = lay.d[m + 1], ldw = lay.ldw[m];
+    const float* W = params + lay.woff[m];
+    uint8_t* img = images + (size_t)m * F_IMG_LAYER;
+    __half* fhi = reinterpret_cast<__half*>(img);
+    __half* flo = reinterpret_cast<__half*>(img + F_IMG_HALF);
+    __half* ahi = reinterpret_cast<__half*>(img + F_IMG);
+    __half* alo = reinterpret_cast<__half*>(img + F_IMG + F_IMG_HALF);
+    const int e = (blockIdx.x & 15) * 256 + threadIdx.x;
+    const int i = e >> 6, j = e & 63;
+    const float w = (i < din && j < dout) ? W[(size_t)i * ldw + j] : 0.f;
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn((w - __half2float(h)) * LO_SCALE);
+    const int of = (i >> 3) * 512 + j * 8 + (i & 7), oa = (j >> 3) * 512 + i * 8 + (j & 7);
+    fhi[of] = h; flo[of] = l;
+    ahi[oa] = h; alo[oa] = l;
+}
+
+struct TcfArgs {
+    PeResidArgs r;
+    const uint8_t* images;
+    pe_term_desc term2;
+    const float* points2;
+    const float* aux2;
+    int n2;
+    float inv_n2;
+    unsigned long long* prof;   // PROF instantiation: 32 cycle counters (0..15 epilogue thread 0, 16..31 issuer) of CTA 0
+};
+
+#define TCF_PROF(slot) do { if (PROF) { if (prof_on) { const long long now_ = clock64(); atomicAdd(args.prof + (slot), (unsigned long long)(now_ - prof_t)); prof_t = now_; } } } while (0)
+
+// MMAs of one layer GEMM for streams [k0, k0 + nk): per K-step of 16 the two cross products, then the hi x hi products (the first of them
+// scales the accumulated cross products by 2^-11); K-steps interleaved across the streams of the call, so that consecutive MMAs do not
+// accumulate into the same tile when the group has more than one stream.
+__device__ __forceinline__ void issue_streams(int k0, int nk, uint32_t tbase, uint32_t act_s, uint32_t img_s, int N, int kdim) {
+    const int ksteps = (kdim + 15) >> 4;
+    const uint32_t id = idesc_km(N);
+#pragma unroll 1
+    for (int s = 0; s < ksteps; ++s) {
+        const uint64_t bhi = sdesc(img_s + 2 * s * 1024, 1024, 128), blo = sdesc(img_s + F_IMG_HALF + 2 * s * 1024, 1024, 128);
+#pragma unroll
+        for (int k = 0; k < TC_MAX_STREAMS; ++k)
+            if (k < nk) mma_bf16_ss(tbase + T_ACC + 64u * (k0 + k), sdesc(act_s + (uint32_t)((k0 + k) * F_STREAM + 2 * s * F_CH), F_CH, 128), blo, id, s > 0);
+#pragma unroll
+        for (int k = 0; k < TC_MAX_STREAMS; ++k)
+            if (k < nk) mma_bf16_ss(tbase + T_ACC + 64u * (k0 + k), sdesc(act_s + (uint32_t)((k0 + k) * F_STREAM + F_PLANE + 2 * s * F_CH), F_CH, 128), bhi, id, 1u);
+    }
+#pragma unroll 1
+    for (int s = 0; s < ksteps; ++s) {
+        const uint64_t bhi = sdesc(img_s + 2 * s * 1024, 1024, 128);
+#pragma unroll
+        for (int k = 0; k < TC_MAX_STREAMS; ++k)
+            if (k < nk) {
+                const uint64_t a = sdesc(act_s + (uint32_t)((k0 + k) * F_STREAM + 2 * s * F_CH), F_CH, 128);
+                if (s == 0) mma_f16_ss_scaled11(tbase + T_ACC + 64u * (k0 + k), a, bhi, id);
+                else mma_bf16_ss(tbase + T_ACC + 64u * (k0 + k), a, bhi, id, 1u);
+            }
+    }
+}
+
+template <int NS, bool PROF>
+__global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int STASH_LAYER = NS * F_STREAM;                 // bytes per stashed layer: NS x (hi plane | lo plane)
+    const PeResidArgs& A = args.r;
+    const PeLayout& lay = A.lay;
+    const pe_term_desc& T = A.term;
+    const pe_term_desc& T2 = args.term2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = lay.L;
+    const bool prof_on = PROF && args.prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == F_EPI);
+    long long prof_t = 0;
+    (void)prof_on; (void)prof_t;
+    uint8_t* act = smem + F_ACT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + F_MISC + B_TMEM);
+    float* tile_scale = reinterpret_cast<float*>(smem + F_MISC + B_SCALE);      // [0..3]: per-warp seed maxima of the tile
+    float* coord = reinterpret_cast<float*>(smem + F_COORD);
+    float* red = reinterpret_cast<float*>(smem + F_RED);
+    float* sbias = reinterpret_cast<float*>(smem + F_BIAS);
+    float* sw0 = reinterpret_cast<float*>(smem + F_W0);
+    const uint32_t act_s = smem_u32(act), r_s = smem_u32(smem + F_R), stg_s = smem_u32(smem + F_STG), ones_s = smem_u32(smem + F_ONES);
+    const uint32_t bar0 = smem_u32(smem + F_MISC);
+    const uint32_t bar_acc = bar0 + B_ACC, bar_act = bar0 + B_ACT, bar_img = bar0 + B_IMG;
+    const uint32_t bar_sfull = bar0 + B_SFULL, bar_sempty = bar0 + B_SEMPTY, bar_dw = bar0 + B_DW;
+
+    for (int i = tid; i < F_TOTAL / 16; i += F_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int slot = A.slot_base + blockIdx.x;
+    float* gpart = A.grad_partials + (size_t)slot * lay.total;
+    uint8_t* stash = reinterpret_cast<uint8_t*>(A.stash + (size_t)blockIdx.x * A.stash_floats);
+    const float* __restrict__ params = A.params;
+    for (int i = tid; i < lay.total; i += F_THREADS) __stcg(gpart + i, 0.f);
+    __syncthreads();
+    for (int i = tid; i < 512; i += F_THREADS) reinterpret_cast<__half*>(smem + F_ONES)[i] = __float2half_rn(1.f);
+    if (tid < 64) {                                  // first-layer weights (3 x d1) and bias -> smem, once per launch
+        const bool in = tid < lay.d[1];
+        sw0[tid] = in ? __ldg(params + lay.woff[0] + tid) : 0.f;
+        sw0[64 + tid] = in ? __ldg(params + lay.woff[0] + lay.ldw[0] + tid) : 0.f;
+        sw0[128 + tid] = in ? __ldg(params + lay.woff[0] + 2 * lay.ldw[0] + tid) : 0.f;
+        sw0[192 + tid] = in ? __ldg(params + lay.boff[0] + tid) : 0.f;
+    }
+    for (int i = tid; i < L * 64; i += F_THREADS) {  // all biases (pads zero)
+        const int m = i >> 6, j = i & 63;
+        sbias[i] = (j < lay.d[m + 1]) ? __ldg(params + lay.boff[m] + j) : 0.f;
+    }
+    if (tid == 0) {
+        for (int g = 0; g < 3; ++g) { mbar_init(bar_acc + 8 * g, 1); mbar_init(bar_act + 8 * g, F_EPI); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_img + 8 * b, 1); mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, 1); }
+        mbar_init(bar_dw, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == F_CTRL) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_async_smem();                              // zero-filled regions and the ones block before any async-proxy access
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tbase = *tmem_slot;
+    const int ntiles_main = (A.n + TC_P - 1) / TC_P;
+    const int ntiles = ntiles_main + (args.n2 + TC_P - 1) / TC_P;
+    // forward image of matrix i-1 (i = 2..L) lives in buffer i & 1 of the region F_R
+    auto fwd_src = [&](int i) { return args.images + (size_t)(i - 1) * F_IMG_LAYER; };
+    auto adj_src = [&](int l) { return args.images + (size_t)(l - 1) * F_IMG_LAYER + F_IMG; };      // adjoint image of matrix l-1 (layer l)
+
+    if (warp >= F_CTRL) {
+        // ============================================================================================ control warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        if (warp == F_CTRL && lane == 0) {
+            uint32_t pact = 0, pimg = 0, psfull = 0, psempty = 0;     // parity bits of the phases this thread waits for next
+            uint32_t n_acc2 = 0, n_dw = 0;
+            auto load_fwd = [&](int i) {
+                const uint32_t b = (uint32_t)(i & 1);
+                mbar_expect_tx(bar_img + 8 * b, F_IMG);
+                tma_load_1d(r_s + b * F_IMG, fwd_src(i), F_IMG, bar_img + 8 * b);
+            };
+            auto wait_img = [&](uint32_t b) { mbar_wait(bar_img + 8 * b, (pimg >> b) & 1u); pimg ^= 1u << b; };
+            auto wait_act = [&](int g) { mbar_wait(bar_act + 8 * g, (pact >> g) & 1u); pact ^= 1u << g; };
+            load_fwd(2);
+            if (L >= 3) load_fwd(3);
+            if (PROF) prof_t = clock64();
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                // ---------------------------------------------------------------- forward: layers 2..L, group by group
+                for (int l = 2; l <= L; ++l) {
+                    const uint32_t b = (uint32_t)(l & 1);
+                    const int NF = (lay.d[l] <= 16) ? 16 : 64;
+                    wait_img(b);
+                    TCF_PROF(16);
+#pragma unroll 1
+                    for (int g = 0; g < 3; ++g) {
+                        wait_act(g);
+                        TCF_PROF(17 + 2 * g);
+                        fence_after();
+                        issue_streams(grp_first<NS>(g), grp_count<NS>(g), tbase, act_s, r_s + b * F_IMG, NF, lay.d[l - 1]);
+                        mma_commit(bar_acc + 8 * g);
+                        TCF_PROF(18 + 2 * g);
+                        if (g == 2) ++n_acc2;
+                        if (g == 0 && l >= 3 && l + 1 <= L) {
+                            // every MMA of layer l-1 precedes G0 of layer l in the pipe: once its last group is complete its image buffer
+                            // (= the buffer of image l + 1) is free
+                            mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
+                            load_fwd(l + 1);
+                            TCF_PROF(23);
+                        }
+                    }
+                }
+                // ---------------------------------------------------------------- reverse sweep: layers L..2
+                // the region F_R changes hands: wait until the output-layer MMAs (the last readers of a forward image) are complete
+                mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
+                mbar_expect_tx(bar_img, F_IMG);
+                tma_load_1d(r_s, adj_src(L), F_IMG, bar_img);
+                for (int l = L; l >= 2; --l) {
+                    const int dout = lay.d[l];
+                    const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;     // outputs of layer l-1 = inputs A of layer l
+                    auto load_stage = [&](int k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_expect_tx(bar_sfull + 8 * sb, F_STREAM);
+                        tma_load_1d(stg_s + sb * F_STREAM, stash_in + (size_t)k * F_STREAM, F_STREAM, bar_sfull + 8 * sb);
+                    };
+                    load_stage(0);                          // both staging buffers are free: the previous layer's DW phase is complete
+                    load_stage(1);
+                    wait_img(0);
+                    TCF_PROF(24);
+                    wait_act(0); wait_act(1); wait_act(2);
+                    TCF_PROF(25);
+                    fence_after();
+                    issue_streams(0, NS, tbase, act_s, r_s, 64, dout);
+                    mma_commit(bar_acc);
+                    mma_commit(bar_acc + 8);
+                    mma_commit(bar_acc + 16);
+                    ++n_acc2;
+                    TCF_PROF(26);
+                    // ---- weight gradient  dW = sum_k A_k^T Zbar_k  (K = 128 points, 8 K-steps of 16): columns 0..55 of the tile take Ah^T Zh,
+                    //      columns 56..111 the cross products Ah^T Zl + Al^T Zh (factor 2^11, resolved when the tile is drained)
+                    const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
+                    const uint32_t id112 = idesc_mn(112), id56 = idesc_mn(56), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
+#pragma unroll 1
+                    for (int k = 0; k < NS; ++k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
+                        psfull ^= 1u << sb;
+                        const uint32_t a_hi = stg_s + sb * F_STREAM, a_lo = a_hi + F_PLANE;
+                        const uint32_t z_hi = act_s + (uint32_t)(k * F_STREAM), z_lo = z_hi + F_PLANE;
+#pragma unroll 1
+                        for (int s = 0; s < 8; ++s) {
+                            const uint32_t o = (uint32_t)(s * 256);          // 16 points x 16 B
+                            const uint64_t dah = sdesc(a_hi + o, 128, F_CH), dal = sdesc(a_lo + o, 128, F_CH);
+                            const uint64_t dzh = sdesc(z_hi + o, 128, F_CH), dzl = sdesc(z_lo + o, 128, F_CH);
+                            const uint32_t first = (k > 0 || s > 0) ? 1u : 0u;
+                            if (nzc == 7) {                                  // [Zh | Zl] are contiguous: one N = 112 MMA
+                                mma_bf16_ss(tbase + T_DW, dah, dzh, id112, first);
+                                mma_bf16_ss(tbase + T_DW + 56, dal, dzh, id56, 1u);
+                            } else {
+                                mma_bf16_ss(tbase + T_DW, dah, dzh, idz, first);
+                                mma_bf16_ss(tbase + T_DW + 56, dah, dzl, idz, first);
+                                mma_bf16_ss(tbase + T_DW + 56, dal, dzh, idz, 1u);
+                            }
+                        }
+                        if (k + 2 < NS) mma_commit(bar_sempty + 8 * sb);       // this buffer is refilled (stream k + 2) once its MMAs are complete
+                        if (k >= 1 && k + 1 < NS) {                          // ... which is waited for one stream later, behind the next stream's MMAs
+                            const uint32_t ob = sb ^ 1u;
+                            mbar_wait(bar_sempty + 8 * ob, (psempty >> ob) & 1u);
+                            psempty ^= 1u << ob;
+                            load_stage(k + 1);
+                        }
+                    }
+                    {   // bias gradient: column 0 of  Zh^T 1  (and of  Zl^T 1): the value-stream plane is the MN-major A operand (M = 64 units;
+                        // its eighth chunk is the first chunk of the lo plane: rows 56..63, ignored), a block of ones the B operand
+                        const uint32_t z_hi = act_s, z_lo = act_s + F_PLANE;
+                        const uint64_t d1 = sdesc(ones_s, 128, 256);
+#pragma unroll 1
+                        for (int s = 0; s < 8; ++s) {
+                            const uint32_t o = (uint32_t)(s * 256);
+                            mma_bf16_ss(tbase + T_BIAS, sdesc(z_hi + o, 128, F_CH), d1, id8, s > 0 ? 1u : 0u);
+                            mma_bf16_ss(tbase + T_BIAS + 8, sdesc(z_lo + o, 128, F_CH), d1, id8, s > 0 ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(bar_dw);
+                    ++n_dw;
+                    TCF_PROF(27);
+                    mbar_wait(bar_dw, (n_dw - 1) & 1u);      // adjoint image, staging buffers and the Zbar planes are free again
+                    TCF_PROF(28);
+                    if (l > 2) {
+                        mbar_expect_tx(bar_img, F_IMG);
+                        tma_load_1d(r_s, adj_src(l - 1), F_IMG, bar_img);
+                    } else if (tile + (int)gridDim.x < ntiles) {
+                        load_fwd(2);
+                        if (L >= 3) load_fwd(3);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================================================================================ epilogue warps
+#if TCF_EW == 8
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+#else
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+#endif
+        const int p = 32 * (warp & 3) + lane;            // TMEM lane = point of the tile
+        const int h = warp >> 2;                         // unit group: 4-unit groups [n4 h / F_NH, n4 (h + 1) / F_NH) of a layer with n4 groups
+        const uint32_t tlane = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+        uint32_t pacc = 0, pdw = 0;
+        auto wait_acc = [&](int g) { mbar_wait(bar_acc + 8 * g, (pacc >> g) & 1u); pacc ^= 1u << g; };
+        auto publish = [&](int g) { mbar_arrive(bar_act + 8 * g); };
+        // planes in shared memory and in the stash (global) were written through the generic proxy; their next readers are MMAs and bulk
+        // copies (async proxy)
+        auto publish_fences = [&]() { asm volatile("fence.proxy.async;" ::: "memory"); fence_before(); };
+        auto c4_lo = [&](int d) { return ((d + 3) >> 2) * h / F_NH; };
+        auto c4_hi = [&](int d) { return ((d + 3) >> 2) * (h + 1) / F_NH; };
+        float tsum[PE_MAX_TERMS], tsum2[PE_MAX_TERMS];
+#pragma unroll
+        for (int i = 0; i < PE_MAX_TERMS; ++i) { tsum[i] = 0.f; tsum2[i] = 0.f; }
+        // 4 units (group c4) of stream k of this thread's point -> hi / lo planes in shared memory [and in the stash layer `st`]
+        auto put4 = [&](uint8_t* st, int k, int c4, const float (&v)[4]) {
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            const int o = k * F_STREAM + (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
+            *reinterpret_cast<uint2*>(act + o) = hi;
+            *reinterpret_cast<uint2*>(act + o + F_PLANE) = lo;
+            if (st) {
+                __stcg(reinterpret_cast<uint2*>(st + o), hi);
+                __stcg(reinterpret_cast<uint2*>(st + o + F_PLANE), lo);
+            }
+        };
+        auto get4 = [&](int k, int c4, float (&v)[4]) {          // this thread's own entries of the planes in shared memory
+            const int o = k * F_STREAM + (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
+            join4(*reinterpret_cast<const uint2*>(act + o), *reinterpret_cast<const uint2*>(act + o + F_PLANE), v);
+        };
+
+        if (PROF) prof_t = clock64();
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const bool sec = tile >= ntiles_main;                          // tile of the fused primal-only set (CTA-uniform)
+            const pe_term_desc& Tc = sec ? T2 : T;
+            const int pt = (sec ? tile - ntiles_main : tile) * TC_P + p;
+            const bool valid = pt < (sec ? args.n2 : A.n);
+            const float* row = (sec ? args.points2 : A.points) + (size_t)(valid ? pt : 0) * Tc.ld;
+            if (h == 0) {
+                float x = 0.f, y = 0.f, t = 0.f;
+                if (valid) { x = row[0]; y = row[1]; t = row[2]; }
+                *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(fmaf(x, Tc.in_scale[0], Tc.in_shift[0]), fmaf(y, Tc.in_scale[1], Tc.in_shift[1]),
+                                                                        fmaf(t, Tc.in_scale[2], Tc.in_shift[2]), valid ? 1.f : 0.f);
+            } else if (h == 1) {
+                const int nt = tile + (int)gridDim.x;                      // pull this CTA's next tile towards L2
+                if (nt < ntiles) {
+                    const bool nsec = nt >= ntiles_main;
+                    const int npt = (nsec ? nt - ntiles_main : nt) * TC_P + p;
+                    if (npt < (nsec ? args.n2 : A.n)) {
+                        const float* nrow = (nsec ? args.points2 : A.points) + (size_t)npt * (nsec ? T2.ld : T.ld);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+                        if (!nsec && A.aux) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.aux + (size_t)npt * 50));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.aux + (size_t)npt * 50 + 32));
+                        }
+                    }
+                }
+            }
+            named_bar_sync(1, F_EPI);
+            // ================================================================ layer 1 (3 -> d1): per-thread FFMA, all streams
+            {
+                const float4 c4v = *reinterpret_cast<const float4*>(coord + 4 * p);
+                const int d1 = lay.d[1];
+#pragma unroll 1
+                for (int c4 = c4_lo(d1); c4 < c4_hi(d1); ++c4) {
+                    float o[NS][4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = 4 * c4 + u;                           // pads: zero weights and bias -> tanh(0) = 0, zero derivatives
+                        float z[NS];
+                        const float w0 = sw0[j], w1 = sw0[64 + j], w2 = sw0[128 + j];
+                        z[0] = fmaf(c4v.x, w0, fmaf(c4v.y, w1, c4v.z * w2));
+                        z[1] = Tc.in_scale[0] * w0; z[2] = Tc.in_scale[1] * w1; z[3] = Tc.in_scale[2] * w2;
+                        if (NS == 5) z[NS - 1] = 0.f;
+                        act_fwd<NS, true>(z, sw0[192 + j]);
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) o[k][u] = z[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) put4(stash, k, c4, o[k]);                 // stash layer 0 = outputs of layer 1
+                }
+                publish_fences();
+                publish(0); publish(1); publish(2);
+                TCF_PROF(0);
+            }
+            // ================================================================ forward: hidden layers 2..L-1, one stream group at a time
+            for (int l = 2; l < L; ++l) {
+                const int lo4 = c4_lo(lay.d[l]), hi4 = c4_hi(lay.d[l]);
+                const float* bl = sbias + (l - 1) * 64;
+                uint8_t* st = stash + (size_t)(l - 1) * STASH_LAYER;
+                // ---- G0: a = tanh(z_0 + b)      (pad units: zero weight columns and bias -> exactly 0)
+                wait_acc(0);
+                TCF_PROF(1);
+                fence_after();
+#pragma unroll 1
+                for (int c4 = lo4; c4 < hi4; ++c4) {
+                    float z[4];
+                    tm_ld4(tlane + T_ACC + 4 * c4, z);
+                    const float4 b4 = *reinterpret_cast<const float4*>(bl + 4 * c4);
+                    tm_wait_ld();
+                    z[0] = tanh_branchfree(z[0] + b4.x); z[1] = tanh_branchfree(z[1] + b4.y);
+                    z[2] = tanh_branchfree(z[2] + b4.z); z[3] = tanh_branchfree(z[3] + b4.w);
+                    put4(st, 0, c4, z);
+                }
+                publish_fences();
+                publish(0);
+                TCF_PROF(2);
+                // ---- G1: a_x = s z_x, a_y = s z_y   (a re-read from this thread's own entries of the value planes)
+                wait_acc(1);
+                TCF_PROF(3);
+                fence_after();
+#pragma unroll 1
+                for (int c4 = lo4; c4 < hi4; ++c4) {
+                    float av[4], z1[4], z2[4];
+                    tm_ld4(tlane + T_ACC + 64 + 4 * c4, z1);
+                    tm_ld4(tlane + T_ACC + 128 + 4 * c4, z2);
+                    get4(0, c4, av);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float s = fmaf(-av[u], av[u], 1.f);
+                        z1[u] *= s;
+                        z2[u] *= s;
+                    }
+                    put4(st, 1, c4, z1);
+                    put4(st, 2, c4, z2);
+                }
+                publish_fences();
+                publish(1);
+                TCF_PROF(4);
+                // ---- G2: a_t = s z_t [, a_tt = s z_tt - 2 a a_t z_t]
+                wait_acc(2);
+                TCF_PROF(5);
+                fence_after();
+#pragma unroll 1
+                for (int c4 = lo4; c4 < hi4; ++c4) {
+                    float av[4], z3[4], z4[4];
+                    tm_ld4(tlane + T_ACC + 192 + 4 * c4, z3);
+                    if (NS == 5) tm_ld4(tlane + T_ACC + 256 + 4 * c4, z4);
+                    get4(0, c4, av);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float a = av[u];
+                        const float s = fmaf(-a, a, 1.f);
+                        const float zt = z3[u];
+                        const float at = s * zt;
+                        z3[u] = at;
+                        if (NS == 5) z4[u] = fmaf(s, z4[u], -2.f * a * at * zt);
+                    }
+                    put4(st, 3, c4, z3);
+                    if (NS == 5) put4(st, 4, c4, z4);
+                }
+                publish_fences();
+                publish(2);
+                TCF_PROF(6);
+            }
+            // ================================================================ output layer L: residuals, loss partials, seeds
+            float inv_sigma = 1.f;
+            {
+                const int dout = lay.d[L];
+                const float* bl = sbias + (L - 1) * 64;
+                wait_acc(0); wait_acc(1); wait_acc(2);
+                TCF_PROF(7);
+                fence_after();
+                float Y[NS][PE_UJ];
+                float amax = 0.f;
+                if (h == 0) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        float v[8];
+                        tm_ld8(tlane + T_ACC + 64 * k, v);
+                        tm_wait_ld();
+#pragma unroll
+                        for (int u = 0; u < PE_UJ; ++u) Y[k][u] = (u < 8 && u < dout) ? v[u < 8 ? u : 0] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += bl[u];
+                    if (!sec) {
+                        const float* aux_row = (NS == 5 && A.aux) ? A.aux + (size_t)(valid ? pt : 0) * 50 : nullptr;
+                        residual_stage<NS>(Y, T, aux_row, row, valid, A.inv_n, tsum);
+                    } else {    // primal-only set: residual on the value stream, zero seeds for the derivative streams
+                        float Y1[1][PE_UJ];
+#pragma unroll
+                        for (int u = 0; u < PE_UJ; ++u) Y1[0][u] = Y[0][u];
+                        const float* aux_row = args.aux2 ? args.aux2 + (size_t)(valid ? pt : 0) * 10 : nullptr;
+                        residual_stage<1>(Y1, T2, aux_row, row, valid, args.inv_n2, tsum2);
+#pragma unroll
+                        for (int u = 0; u < PE_UJ; ++u) {
+                            Y[0][u] = Y1[0][u];
+#pragma unroll
+                            for (int k = 1; k < NS; ++k) Y[k][u] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NS; ++k)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) amax = fmaxf(amax, fabsf(Y[k][u]));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                    if (lane == 0) tile_scale[warp] = amax;
+                }
+                // the tile's seed scale: sigma = 2^-e with max |seed| * sigma in [1, 2)  (1 when all seeds vanish); identical in every thread
+                named_bar_sync(1, F_EPI);
+                const float m4 = fmaxf(fmaxf(tile_scale[0], tile_scale[1]), fmaxf(tile_scale[2], tile_scale[3]));
+                uint32_t eb = (__float_as_uint(m4) >> 23) & 0xFFu;
+                eb = (m4 > 0.f) ? min(max(eb, 2u), 252u) : 127u;
+                const float sigma = __uint_as_float((254u - eb) << 23);
+                inv_sigma = __uint_as_float(eb << 23);
+                if (h == 0) {
+                    // seeds Zbar_L: units 0..7 in groups 0 and 1 (the only chunk the adjoint / weight-gradient MMAs of the output layer use)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const float v0[4] = {Y[k][0] * sigma, Y[k][1] * sigma, Y[k][2] * sigma, Y[k][3] * sigma};
+                        const float v1[4] = {Y[k][4] * sigma, Y[k][5] * sigma, Y[k][6] * sigma, Y[k][7] * sigma};
+                        put4(nullptr, k, 0, v0);
+                        put4(nullptr, k, 1, v1);
+                    }
+                }
+                publish_fences();
+                publish(0); publish(1); publish(2);
+                TCF_PROF(8);
+            }
+            // ================================================================ reverse sweep, layers L .. 2
+            for (int l = L; l >= 2; --l) {
+                const int m = l - 1;
+                const int din = lay.d[l - 1], dout = lay.d[l];
+                const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;          // outputs of layer l-1 = inputs A of layer l
+                const int lo4 = c4_lo(din), hi4 = c4_hi(din);
+                // ---- stashed outputs of layer l-1 for this thread's first unit group: in flight while the MMAs run
+                auto ldst = [&](int k, int c4, uint2& hi, uint2& lo) {
+                    const uint8_t* src = stash_in + (size_t)k * F_STREAM + (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
+                    hi = __ldcg(reinterpret_cast<const uint2*>(src));
+                    lo = __ldcg(reinterpret_cast<const uint2*>(src + F_PLANE));
+                };
+                uint2 nh[NS], nl[NS];
+                if (lo4 < hi4) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) ldst(k, lo4, nh[k], nl[k]);
+                }
+                wait_acc(0); wait_acc(1); wait_acc(2);       // adjoint MMAs done: abar^{l-1} in the accumulators
+                TCF_PROF(9);
+                mbar_wait(bar_dw, pdw);                      // weight / bias gradient MMAs done: the Zbar_l planes may be overwritten
+                pdw ^= 1u;
+                TCF_PROF(10);
+                fence_after();
+                {   // drain: weight-gradient rows i = 16*quadrant + lane (lane < 16); the unit groups share the columns; bias gradient = column 0
+                    const int quad = warp & 3;
+                    const int i = 16 * quad + lane;
+                    const int ldw = lay.ldw[m];
+                    float* gW = gpart + lay.woff[m];
+                    float* gB = gpart + lay.boff[m];
+                    const int nc8 = (dout + 7) >> 3;
+                    for (int c8 = h; c8 < nc8; c8 += F_NH) {
+                        const int c = 8 * c8;
+                        float v[8], vx[8];
+                        tm_ld8(tlane + T_DW + c, v);
+                        tm_ld8(tlane + T_DW + 56 + c, vx);
+                        tm_wait_ld();
+                        if (lane < 16 && i < din) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = fmaf(vx[q], LO_INV, v[q]) * inv_sigma;
+                            float* dst = gW + (size_t)i * ldw + c;
+                            if (c < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+                            if (c + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+                        }
+                    }
+                    if (h == F_NH - 1) {
+                        float vb[8], vbx[8];
+                        tm_ld8(tlane + T_BIAS, vb);
+                        tm_ld8(tlane + T_BIAS + 8, vbx);
+                        tm_wait_ld();
+                        if (lane < 16 && i < dout) atomicAdd(gB + i, fmaf(vbx[0], LO_INV, vb[0]) * inv_sigma);
+                    }
+                }
+                TCF_PROF(11);
+                // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs (hi + lo)
+#pragma unroll 1
+                for (int c4 = lo4; c4 < hi4; ++c4) {
+                    float ab[NS][4], Av[NS][4];
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) tm_ld4(tlane + T_ACC + 64 * k + 4 * c4, ab[k]);
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) join4(nh[k], nl[k], Av[k]);
+                    if (c4 + 1 < hi4) {
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) ldst(k, c4 + 1, nh[k], nl[k]);
+                    }
+                    tm_wait_ld();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float b[NS], Aa[NS];
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) { b[k] = ab[k][u]; Aa[k] = Av[k][u]; }
+                        act_bwd<NS>(b, Aa);                   // pad units: abar = 0 and A = 0 -> 0
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) ab[k][u] = b[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) put4(nullptr, k, c4, ab[k]);
+                }
+                if (l > 2) {
+                    publish_fences();
+                    publish(0); publish(1); publish(2);
+                }
+                TCF_PROF(12);
+            }
+            // ================================================================ layer 1 gradient (3 x d1 + bias): FFMA, fixed-order reduce
+            named_bar_sync(1, F_EPI);
+            {
+                const int d1 = lay.d[1];
+                const int j = tid & 63, qq = tid >> 6;                    // 4 point quarters x 64 units
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gb = 0.f;
+                if (j < d1 && tid < 256) {
+                    const uint8_t* base = act + (j >> 3) * F_CH + (j & 7) * 2;
+#pragma unroll 4
+                    for (int s = 0; s < 32; ++s) {
+                        const int pp = 32 * qq + s;
+                        const float4 c4v = *reinterpret_cast<const float4*>(coord + 4 * pp);
+                        auto val = [&](int k) {
+                            const uint8_t* q = base + k * F_STREAM + pp * 16;
+                            return fmaf(__half2float(*reinterpret_cast<const __half*>(q + F_PLANE)), LO_INV, __half2float(*reinterpret_cast<const __half*>(q)));
+                        };
+                        const float zv = val(0), zx = val(1), zy = val(2), zt = val(3);
+                        g0 = fmaf(c4v.x, zv, fmaf(Tc.in_scale[0], zx, g0));
+                        g1 = fmaf(c4v.y, zv, fmaf(Tc.in_scale[1], zy, g1));
+                        g2 = fmaf(c4v.z, zv, fmaf(Tc.in_scale[2], zt, g2));
+                        gb += zv;
+                    }
+                }
+                if (tid < 256) *reinterpret_cast<float4*>(red + (qq * 64 + j) * 4) = make_float4(g0 * inv_sigma, g1 * inv_sigma, g2 * inv_sigma, gb * inv_sigma);
+                named_bar_sync(1, F_EPI);
+                if (tid < 64 && tid < d1) {
+                    float4 s = *reinterpret_cast<float4*>(red + tid * 4);
+#pragma unroll
+                    for (int r = 1; r < 4; ++r) {
+                        const float4 v = *reinterpret_cast<float4*>(red + (r * 64 + tid) * 4);
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    }
+                    float* gW = gpart + lay.woff[0];
+                    const int ldw = lay.ldw[0];
+                    __stcg(gW + tid, __ldcg(gW + tid) + s.x);
+                    __stcg(gW + ldw + tid, __ldcg(gW + ldw + tid) + s.y);
+                    __stcg(gW + 2 * ldw + tid, __ldcg(gW + 2 * ldw + tid) + s.z);
+                    float* gB = gpart + lay.boff[0];
+                    __stcg(gB + tid, __ldcg(gB + tid) + s.w);
+                }
+                named_bar_sync(1, F_EPI);
+            }
+            TCF_PROF(13);
+        }
+        // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem (fixed order)
+        {
+            float tot[2 + PE_MAX_TERMS];
+            tot[0] = warp_sum(tsum[0]);
+            tot[1] = warp_sum(tsum[1]);
+#pragma unroll
+            for (int c = 0; c < PE_MAX_TERMS; ++c) tot[2 + c] = warp_sum(tsum2[c]);
+            named_bar_sync(1, F_EPI);
+            if (h == 0 && lane == 0) {
+#pragma unroll
+                for (int c = 0; c < 2 + PE_MAX_TERMS; ++c) red[(2 + PE_MAX_TERMS) * warp + c] = tot[c];
+            }
+            named_bar_sync(1, F_EPI);
+            if (tid == 0) {
+                float* tp = A.term_partials + (size_t)slot * PE_MAX_TERMS;
+#pragma unroll
+                for (int i = 0; i < PE_MAX_TERMS; ++i) tp[i] = 0.f;
+                auto S = [&](int c) { const int st = 2 + PE_MAX_TERMS; return red[c] + red[st + c] + red[2 * st + c] + red[3 * st + c]; };
+                tp[T.term[0]] += S(0) * A.inv_n;
+                tp[T.term[1]] += S(1) * A.inv_n;
+                if (args.n2 > 0) {
+                    const int nres2 = (T2.kind == PE_RES_TRACTION) ? 1 : T2.ncols;
+                    for (int c = 0; c < nres2; ++c) tp[T2.term[c]] += S(2 + c) * args.inv_n2;
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == F_CTRL) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
+template <int NS, bool PROF>
+int launch_tcf(const TcfArgs& t, int slots, cudaStream_t st) {
+    auto kern = resid_tcf_kernel<NS, PROF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F_TOTAL);
+    if (e != cudaSuccess) { pe_set_error("cudaFuncSetAttribute(resid_tcf, %d): %s", F_TOTAL, cudaGetErrorString(e)); return 2; }
+    kern<<<slots, F_THREADS, F_TOTAL, st>>>(t);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { pe_set_error("launch resid_tcf<%d>: %s", NS, cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
+}  // namespace
+
+size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
+
+static unsigned long long* g_tcf_prof = nullptr;
+extern "C" void pe_debug_set_tcf_profile(unsigned long long* d_counters32) { g_tcf_prof = d_counters32; }
+
+// Scratch layout (d_stash of the C ABI): [slots][stash floats per slot] then the operand images.  Per slot: (L-1) layers x 5 streams x
+// F_STREAM bytes (the planes are stashed as they are).
+int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
+                        const pe_term_desc* term2, const float* points2, int n2, const float* aux2) {
+    TcfArgs t;
+    t.r = a;
+    t.n2 = 0; t.points2 = nullptr; t.aux2 = nullptr; t.inv_n2 = 0.f;
+    memset(&t.term2, 0, sizeof(t.term2));
+    if (term2 && n2 > 0) {
+        t.term2 = *term2; t.points2 = points2; t.n2 = n2; t.aux2 = term2->aux_k ? aux2 : nullptr;
+        t.inv_n2 = 1.0f / (float)term2->n_global;
+    }
+    if (plan->lay.L < 3) { pe_set_error("tcf engine: needs at least two hidden layers"); return 1; }
+    t.prof = g_tcf_prof;
+    t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
+    uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
+    t.images = images;
+    tcf_image_kernel<<<plan->lay.L * 16, 256, 0, st>>>(a.params, a.lay, images);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { pe_set_error("tcf_image_kernel: %s", cudaGetErrorString(e)); return 3; }
+    if (K == 5) return g_tcf_prof ? launch_tcf<5, true>(t, slots, st) : launch_tcf<5, false>(t, slots, st);
+    if (K == 4) return g_tcf_prof ? launch_tcf<4, true>(t, slots, st) : launch_tcf<4, false>(t, slots, st);
+    pe_set_error("tcf engine: K = %d not instantiated (4 or 5)", K);
+    return 1;
+}

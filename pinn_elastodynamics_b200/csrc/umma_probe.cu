@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs a) {
             uint64_t da = a.a_desc[i], db = a.b_desc[i];
             db = (db & ~0x3FFFull) | (((db & 0x3FFF) + base16) & 0x3FFF);
             uint32_t d = tbase + a.d_col[i], id = a.idesc[i], acc = a.accum[i], kind = a.kind[i];
-            if (kind < 2) da = (da & ~0x3FFFull) | (((da & 0x3FFF) + base16) & 0x3FFF);
-            if (kind >= 4) db = 0;
+            if (kind < 2 || kind == 6) da = (da & ~0x3FFFull) | (((da & 0x3FFF) + base16) & 0x3FFF);
+            if (kind == 4 || kind == 5) db = 0;
             uint32_t ta = tbase + (uint32_t)(da & 0xFFFFFFFFu);
             if (kind == 0)
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d), "l"(da), "l"(db), "r"(id), "r"(acc) : "memory");
@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs a) {
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(ta), "l"(db), "r"(id), "r"(acc) : "memory");
             else if (kind == 3)
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(ta), "l"(db), "r"(id), "r"(acc) : "memory");
+            else if (kind == 6)        // kind::f16 SS with scale-input-d: D = A B + D * 2^-11
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n}" ::"r"(d), "l"(da), "l"(db), "r"(id), "r"(acc) : "memory");
             else if (kind == 4) {      // smem -> TMEM copy, 128 lanes x 256 bit; a_desc = smem matrix descriptor, d_col = target column
                 uint64_t dc = (a.a_desc[i] & ~0x3FFFull) | (((a.a_desc[i] & 0x3FFF) + base16) & 0x3FFF);
                 asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(d), "l"(dc) : "memory");

@@ -25,7 +25,7 @@ def relv(a, b):
     return float(np.max(np.abs(a - b) / np.abs(b)))
 
 
-for engine in ('simt', 'tc3s'):
+for engine in (sys.argv[1:] or ('simt', 'tc3s')):
     for composite in (False, True):
         S = {k: G['plate_' + k] for k in ('Collo', 'HOLE', 'IC', 'LF', 'RT', 'UP', 'LW', 'DIST', 'lb', 'ub')}
         Ws, bs = uv('plate')

@@ -239,6 +239,103 @@ def t_tf32_truncation():
     return float(out[0, 0])
 
 
+def t_f16_scaled_d(K=64, N=64):
+    """round 2: the scale-input-d form of tcgen05.mma (kind 6 of the probe kernel: D = A B + D * 2^-11).  Sequence of the fp16-pair engine:
+    lo products accumulate first, then the first hi x hi K-step scales them down by 2^11, the other hi x hi K-steps accumulate plainly."""
+    rng = np.random.default_rng(11)
+    A1 = rng.integers(-3, 4, (128, K)).astype(np.float32); B1 = rng.integers(-3, 4, (N, K)).astype(np.float32)
+    A2 = rng.integers(-3, 4, (128, K)).astype(np.float32); B2 = rng.integers(-3, 4, (N, K)).astype(np.float32)
+    imgs = [chunked(f16_bits(m), 8).ravel().view(np.uint8) for m in (A1, B1, A2, B2)]
+    offs = np.cumsum([0] + [i.size for i in imgs])
+    smem = np.concatenate(imgs)
+    mm = [(1, sdesc(offs[0] + s * 4096, 2048, 128), sdesc(offs[1] + s * 2 * N * 16, N * 16, 128), idesc(0, 128, N), 0, 1 if s else 0) for s in range(K // 16)]
+    mm += [(6 if s == 0 else 1, sdesc(offs[2] + s * 4096, 2048, 128), sdesc(offs[3] + s * 2 * N * 16, N * 16, 128), idesc(0, 128, N), 0, 1) for s in range(K // 16)]
+    out = run(smem, mm, N)
+    exp = A2 @ B2.T + (A1 @ B1.T) / 2048.0
+    return np.array_equal(out, exp.astype(np.float32)), out, exp
+
+
+def t_acc_rounding():
+    """how does the tensor core round when it adds a product to the fp32 accumulator?  D = 1.0, then one MMA adds m / 8 ulp(1.0)
+    (m * 2^-26); and one MMA that holds 1.0 and fifteen products of 1/4 ulp each.  Printed in units of ulp(1) = 2^-23."""
+    res = {}
+    ulp = 2.0 ** -23
+    for m in (1, 2, 3, 4, 5, 6, 7, -1, -2, -3, -4, -5, -6, -7):
+        A0 = np.zeros((128, 16), np.float32); B0 = np.zeros((64, 16), np.float32)
+        A0[:, 0] = 1.0; B0[:, 0] = 1.0
+        A1 = np.zeros((128, 16), np.float32); B1 = np.zeros((64, 16), np.float32)
+        A1[:, 0] = m * 2.0 ** -13; B1[:, 0] = 2.0 ** -13
+        imgs = [chunked(f16_bits(x), 8).ravel().view(np.uint8) for x in (A0, B0, A1, B1)]
+        offs = np.cumsum([0] + [i.size for i in imgs])
+        mm = [(1, sdesc(offs[0], 2048, 128), sdesc(offs[1], 1024, 128), idesc(0, 128, 64), 0, 0),
+              (1, sdesc(offs[2], 2048, 128), sdesc(offs[3], 1024, 128), idesc(0, 128, 64), 0, 1)]
+        out = run(np.concatenate(imgs), mm, 64)
+        res['1 + %+d/8 ulp' % m] = (float(out[0, 0]) - 1.0) / ulp
+    A0 = np.zeros((128, 16), np.float32); B0 = np.zeros((64, 16), np.float32)
+    A0[:, 0] = 1.0; B0[:, 0] = 1.0
+    A0[:, 1:] = 2.0 ** -12; B0[:, 1:] = 2.0 ** -13
+    imgs = [chunked(f16_bits(x), 8).ravel().view(np.uint8) for x in (A0, B0)]
+    out = run(np.concatenate(imgs), [(1, sdesc(0, 2048, 128), sdesc(imgs[0].size, 1024, 128), idesc(0, 128, 64), 0, 0)], 64)
+    res['one MMA: 1 + 15 x 1/4 ulp (exact 3.75)'] = (float(out[0, 0]) - 1.0) / ulp
+    # 16 products of equal size 1 + 2^-10 squared etc.: the sum of sixteen (1 + 2^-10)^2 = 16 + 2^-5 + 2^-16 (exact needs 21 bits below the leading bit)
+    A0[:, :] = 1.0 + 2.0 ** -10; B0[:, :] = 1.0 + 2.0 ** -10
+    imgs = [chunked(f16_bits(x), 8).ravel().view(np.uint8) for x in (A0, B0)]
+    out = run(np.concatenate(imgs), [(1, sdesc(0, 2048, 128), sdesc(imgs[0].size, 1024, 128), idesc(0, 128, 64), 0, 0)], 64)
+    res['one MMA: 16 x (1 + 2^-10)^2 - 16 - 2^-5, in units of 2^-16 (exact 1)'] = (float(out[0, 0]) - 16.0 - 2.0 ** -5) / 2.0 ** -16
+    return res
+
+
+def t_mn_f16_concat(N=112, M=64, P=128, a_chunks=7):
+    """weight-gradient tile of the fp16-pair engine: A operand = a 7-chunk fp16 plane read with M = 64 (rows 56..63 fall on whatever follows
+    the plane: finite garbage, ignored), B operand = [Zhi | Zlo] planes, contiguous, read as one N = 112 operand."""
+    rng = np.random.default_rng(12)
+    A = rng.integers(-24, 25, (P, 8 * a_chunks)).astype(np.float32) / 8
+    Z = rng.integers(-24, 25, (P, N)).astype(np.float32) / 8
+    ia, iz = chunked(f16_bits(A), 8), chunked(f16_bits(Z), 8)
+    smem = np.concatenate([ia.ravel().view(np.uint8), iz.ravel().view(np.uint8)])
+    offz = ia.size * 2
+    mm = [(1, sdesc(s * 256, 128, P * 16), sdesc(offz + s * 256, 128, P * 16), idesc(0, M, N, 1, 1), 0, 1 if s else 0) for s in range(P // 16)]
+    out = run(smem, mm, 128)
+    exp = A.T @ Z
+    lanes = np.concatenate([np.arange(16) + 32 * q for q in range(4)])
+    got = out[lanes][:8 * a_chunks, :N]
+    return np.array_equal(got, exp), got, exp
+
+
+def t_kmajor_f16_garbage_chunk(N=64):
+    """layer GEMM of the fp16-pair engine: a 7-chunk activation plane (56 units) read with four K-steps of 16: the eighth chunk is whatever
+    follows the plane (finite), multiplied by weight rows 56..63 that are zero."""
+    rng = np.random.default_rng(13)
+    A = rng.integers(-24, 25, (128, 56)).astype(np.float32) / 8
+    G = rng.integers(-24, 25, (128, 8)).astype(np.float32) / 8            # the garbage chunk
+    B = np.zeros((N, 64), np.float32); B[:, :56] = rng.integers(-24, 25, (N, 56)).astype(np.float32) / 8
+    ia = chunked(f16_bits(np.concatenate([A, G], 1)), 8); ib = chunked(f16_bits(B), 8)
+    smem = np.concatenate([ia.ravel().view(np.uint8), ib.ravel().view(np.uint8)])
+    offb = ia.size * 2
+    mm = [(1, sdesc(s * 4096, 2048, 128), sdesc(offb + s * 2 * N * 16, N * 16, 128), idesc(0, 128, N), 0, 1 if s else 0) for s in range(4)]
+    out = run(smem, mm, N)
+    exp = A @ B[:, :56].T
+    return np.array_equal(out, exp), out, exp
+
+
+def t_ones_bias(P=128, N=8):
+    """bias gradient of the fp16-pair engine: D[j][0] = sum_p Z[p][j] as an MMA with the Z plane as MN-major A operand (M = 64 units) and a
+    block of ones as B (N = 8): K-major B with LBO = SBO = 0 over 16 B of ones would also do, here a plain 256 B block."""
+    rng = np.random.default_rng(14)
+    Z = rng.integers(-24, 25, (P, 56)).astype(np.float32) / 8
+    iz = chunked(f16_bits(Z), 8)
+    ones = np.full(1024, 0x3C00, np.uint16)
+    tail = chunked(f16_bits(rng.integers(-3, 4, (P, 8)).astype(np.float32)), 8)     # what the eighth chunk of the M = 64 read falls on
+    smem = np.concatenate([iz.ravel().view(np.uint8), tail.ravel().view(np.uint8), ones.view(np.uint8)])
+    offo = (iz.size + tail.size) * 2
+    mm = [(1, sdesc(s * 256, 128, P * 16), sdesc(offo, 128, 256), idesc(0, 64, N, 1, 1), 0, 1 if s else 0) for s in range(P // 16)]
+    out = run(smem, mm, 8)
+    lanes = np.concatenate([np.arange(16) + 32 * q for q in range(4)])
+    got = out[lanes][:56, 0]
+    exp = Z.sum(0)
+    return np.array_equal(got, exp), got[None, :], exp[None, :]
+
+
 TESTS = [('kmajor tf32 K=8', lambda: t_kmajor_tf32()), ('kmajor tf32 K=8 swapped LBO/SBO', lambda: t_kmajor_tf32(swap=True)),
          ('kmajor tf32 K=56 N=64', lambda: t_kmajor_tf32(K=56)), ('kmajor tf32 K=56 N=16', lambda: t_kmajor_tf32(K=56, N=16)),
          ('mnmajor tf32 M=64 N=64 P=128', lambda: t_mnmajor_tf32()), ('mnmajor swapped', lambda: t_mnmajor_tf32(swap=True)),
@@ -253,6 +350,11 @@ TESTS = [('kmajor tf32 K=8', lambda: t_kmajor_tf32()), ('kmajor tf32 K=8 swapped
          ('f16 x f16 SS K=64', lambda: t_mixed_16bit_ss(0, 0)), ('f16(A) x bf16(B) SS K=64', lambda: t_mixed_16bit_ss(0, 1)),
          ('bf16(A) x f16(B) SS K=64', lambda: t_mixed_16bit_ss(1, 0)),
          ('mnmajor f16(A) x bf16(Z) M=64 N=56', lambda: t_mixed_16bit_mn(0, 1)), ('mnmajor bf16(A) x f16(Z) M=64 N=56', lambda: t_mixed_16bit_mn(1, 0)),
+         ('f16 scale-input-d (D = A B + D 2^-11)', lambda: t_f16_scaled_d()),
+         ('mnmajor f16 M=64 N=112 concat planes', lambda: t_mn_f16_concat()),
+         ('kmajor f16 7-chunk plane + garbage chunk x zero rows', lambda: t_kmajor_f16_garbage_chunk()),
+         ('ones-block bias gradient M=64 N=8', lambda: t_ones_bias()),
+         ('accumulator rounding', 'acc'),
          ('tf32 conversion', None)]
 
 
@@ -302,7 +404,10 @@ if __name__ == '__main__':
         sys.exit(0)
     nm, fn = TESTS[int(sys.argv[1])]
     try:
-        if fn is None:
+        if fn == 'acc':
+            for k, v in t_acc_rounding().items():
+                print('ACC  %-70s -> %+.4f' % (k, v))
+        elif fn is None:
             print('tf32 operand conversion of 1+2^-11+2^-12 ->', t_tf32_truncation(), '(1.0 = truncation, 1.0009766 = round-to-nearest)')
         else:
             r = fn()

@@ -42,22 +42,24 @@ def _run(layers, K, n, variant, lb=None, ub=None, seed=3):
     return out.cpu().numpy().astype(np.float64), ref
 
 
-@pytest.mark.parametrize('variant', [0, 1])            # 0: zero pad chunk, 1: LBO = 0 on the last K-step
+@pytest.mark.parametrize('variant', [0, 2])            # 0: 8-chunk planes with a zero pad chunk, 2: 7-chunk planes, the last K-step reads past the plane (x zero rows)
+                                                       # (variant 1, LBO = 0 on the last K-step, never completes on B200: the launch hangs until the bounded wait traps)
 @pytest.mark.parametrize('K,O', [(5, 5), (4, 7)])
 def test_forward_jets_on_the_16_bit_split(K, O, variant):
     got, ref = _run([3] + 5 * [50] + [O], K, 1000, variant)
     assert np.isfinite(got).all()
+    print('tc-forward K=%d O=%d variant %d: per-stream rel err' % (K, O, variant), ['%.2e' % (np.abs(got[:, k] - ref[:, k]).max() / max(1e-30, np.abs(ref[:, k]).max())) for k in range(K)])
     for k in range(K):      # per stream: error against that stream's output scale
         assert np.abs(got[:, k] - ref[:, k]).max() <= 1e-5 * max(1e-30, np.abs(ref[:, k]).max()), (k, np.abs(got[:, k] - ref[:, k]).max(), np.abs(ref[:, k]).max())
 
 
 @pytest.mark.parametrize('n', [1, 127, 129, 128 * 149 + 3])
 def test_ragged_point_counts_and_narrow_nets(n):
-    got, ref = _run([3, 14, 30, 5], 5, n, 1)
+    got, ref = _run([3, 14, 30, 5], 5, n, 2)
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
 def test_normalised_inputs():
     lb, ub = np.array([0., 0, 0]), np.array([30., 30, 20.])
-    got, ref = _run([3] + 3 * [50] + [7], 4, 500, 1, lb, ub)
+    got, ref = _run([3] + 3 * [50] + [7], 4, 500, 2, lb, ub)
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
