@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- collocation-point residual+grad evaluations / second per Adam step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine tc3s|tc3p|tc3|simt|tc1s] [--points P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|tcf|tc3s|simt|tc1s] [--points P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1], SURVEY.md 8d "Config 2"): defected plate, plane stress (E=20, mu=.25, rho=1),
@@ -34,9 +34,18 @@ LAYERS = [3] + 5 * [50] + [5]
 S_WEIGHTS = sum(LAYERS[i] * LAYERS[i + 1] for i in range(len(LAYERS) - 1))     # 10,400
 FLOP_PER_POINT = 6 * 5 * S_WEIGHTS                                            # 6*K*S = 312,000
 METRIC = 'collocation-pt residual+grad evals/sec per Adam step'
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures of
-# the default workload (profiles/r1_tc3s_ncu_summary.txt, profiles/r1_tc3_ncu_summary.txt, profiles/r1_simt_ncu_summary.txt); bytes
-TRAFFIC = {'tc3': 112.27e6 + 282.54e6, 'tc3s': 120.89e6 + 285.23e6, 'simt': 17.6e6 + 103.3e6}
+
+
+def measured_traffic(engine, points):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: read from profiles/traffic.json, which is written
+    from an `ncu --set full` capture of THIS build and workload (profiles/summarize.py); None when no capture of that engine / size is
+    committed (a number from another build is not a measurement of this run)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        e = t.get(f'{engine}:{points}')
+        return None if e is None else float(e['dram_bytes_read']) + float(e['dram_bytes_write'])
+    except Exception:
+        return None
 
 
 def make_workload(n_c, seed=1111):
@@ -194,7 +203,7 @@ def main():
     ap.add_argument('--steps', type=int, default=1500)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--engine', default='tc3s', help='tc3s = warp-specialised, stream-pipelined tcgen05 engine (fp32-parity split; default), tc3 / tc3p = first / second generation tcgen05 engines (bit-identical results), simt = fp32 FFMA engine, tc1/tc1p/tc1s = single-pass TF32')
+    ap.add_argument('--engine', default='auto', help="auto = tcf = fp16-pair tcgen05 engine (fp32-grade, what the drop-in classes select by default), tc3s = TF32x3 tcgen05 engine (A/B partner), simt = fp32 FFMA engine, tc1s = single-pass TF32")
     ap.add_argument('--points', type=int, default=50000, help='collocation points per GPU')
     ap.add_argument('--ref-points', type=int, default=10000)
     ap.add_argument('--ref-steps', type=int, default=8)
@@ -227,6 +236,7 @@ def main():
     Ws, bs = xavier_init_lists(LAYERS, np.random.default_rng(1111))
     model.uv_net.set_weights(Ws, bs)
     eng = model.engine
+    ename = 'tcf' if args.engine == 'auto' else args.engine
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 
     def barrier():
@@ -306,15 +316,15 @@ def main():
             'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'defected plate F5 (plane stress), 5x50 tanh mixed-variable net, {args.points} collocation pts/GPU + {HOLE.shape[0] // world} hole pts/GPU, Adam lr 5e-4 (BASELINE configs[1])',
-                       'net': LAYERS, 'global_collocation_points': n_total, 'engine': args.engine, 'parallelism': f'dp{world} (index-sharded points, 1 all-reduce of [grad|terms] per step)',
+                       'net': LAYERS, 'global_collocation_points': n_total, 'engine': ename, 'parallelism': f'dp{world} (index-sharded points, 1 all-reduce of [grad|terms] per step)',
                        'allreduce': None if world == 1 else ('in-kernel over NVLink peer memory, fused with slot reduction and Adam (pe_reduce_peer)' if eng.comm is not None else 'NCCL (reduce -> all_reduce -> Adam)'),
                        'l2': 'flushed between timed steps (256 MiB memset outside the per-step event pairs)'},
             'clocks': clocks,
             'gpu_launches': launches,
             'e2e': e2e,
-            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': TRAFFIC.get(args.engine) if args.points == 50000 else None,
-                         'kernel': {'simt': 'resid_simt_kernel<5>', 'tc3p': 'resid_tcp_kernel<5> (tcgen05, pipelined dW)', 'tc1p': 'resid_tcp_kernel<5> (tcgen05, pipelined dW)',
-                                    'tc3s': 'resid_tcs_kernel<5> (tcgen05, warp-specialised)', 'tc1s': 'resid_tcs_kernel<5> (tcgen05, warp-specialised)'}.get(args.engine, 'resid_tc_kernel (tcgen05)') + ' (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': measured_traffic(ename, args.points),
+                         'kernel': {'simt': 'resid_simt_kernel<5>', 'tcf': 'resid_tcf_kernel<5> (tcgen05, fp16-pair operands)',
+                                    'tc3s': 'resid_tcs_kernel<5> (tcgen05, TF32x3)', 'tc1s': 'resid_tcs_kernel<5> (tcgen05, TF32)'}[ename] + ' (collocation F5)', 'kernel_ms': kms, 'kernel_share_of_step': kms / ms_step,
                          'flop_per_point': FLOP_PER_POINT,
                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in pk else 'fallback',
                          'fp32_ffma_peak_tflops': 148 * 128 * 2 * (clocks['sm_mhz'] or 1965.0) * 1e-6},

@@ -51,22 +51,15 @@ enum {
 /* precision / engine selection for the residual kernels */
 enum {
     PE_ENGINE_SIMT_FP32 = 0,   /* fp32 FFMA kernels: parity anchor, any width */
-    PE_ENGINE_TC_TF32X3 = 1,   /* tcgen05 tensor-core tiles, 3xTF32 split (fp32-parity mode) */
-    PE_ENGINE_TC_TF32 = 2,     /* tcgen05 tensor-core tiles, single-pass TF32 (fast mode) */
-    PE_ENGINE_TCP_TF32X3 = 3,  /* second-generation tcgen05 engine (csrc/pe_tcp.cu): 3xTF32 split, weight-gradient phase as a
-                                  converter-warps / MMA-warp pipeline; PE_RES_F5 (K=5) and PE_RES_F7 (K=4) */
-    PE_ENGINE_TCP_TF32 = 4,    /* same, single-pass TF32 */
-    PE_ENGINE_TCS_TF32X3 = 5,  /* third-generation tcgen05 engine (csrc/pe_tcs.cu): warp-specialised (12 epilogue warps + MMA/TMA issuer
-                                  warp), jet-stream groups pipelined through the forward pass, TMA-fed double-buffered weight images;
-                                  same terms and networks as PE_ENGINE_TCP_* */
-    PE_ENGINE_TCS_TF32 = 6,    /* same, single-pass TF32 */
+    PE_ENGINE_TCS_TF32X3 = 5,  /* TF32x3 tcgen05 engine (csrc/pe_tcs.cu): warp-specialised (12 epilogue warps + MMA/TMA issuer warp), jet-stream
+                                  groups pipelined through the forward pass, TMA-fed double-buffered weight images; PE_RES_F5 (K = 5) and
+                                  PE_RES_F7 (K = 4), hidden widths <= 56.  Measured 5e-6 .. 8e-6 against the reference goldens: kept as the A/B
+                                  partner of PE_ENGINE_TCF, not selected by 'auto' */
+    PE_ENGINE_TCS_TF32 = 6,    /* same, single-pass TF32 (1e-3 class) */
     PE_ENGINE_TCF = 8,         /* fp16-pair tcgen05 engine (csrc/pe_tcf.cu): every GEMM operand as an fp16 pair (hi, lo scaled by 2^11), products
                                   Ah Bh + 2^-11 (Ah Bl + Al Bh) on kind::f16 MMAs with the scale-input-d form, per-tile power-of-two seed
                                   scaling, TMA-fed weight gradient without a conversion pass; PE_RES_F5 (K = 5) and PE_RES_F7 (K = 4), hidden
                                   widths <= 56, at least two hidden layers */
-    PE_ENGINE_TC4 = 7          /* EXPERIMENTAL fourth-generation tcgen05 engine (csrc/pe_tc4.cu): one fp16-hi + bf16-lo operand split
-                                  for forward, adjoint and weight-gradient GEMMs, TMA-fed weight gradient without a conversion pass; written at
-                                  the end of round 1, not yet validated on hardware; opt-in only (never chosen by 'auto') */
 };
 
 typedef struct pe_plan pe_plan; /* host-side description of one network: dims, padded layout, launch config */
@@ -111,9 +104,8 @@ int pe_plan_param_count_padded(const pe_plan *plan);   /* padded device length (
 int pe_plan_weight_offset(const pe_plan *plan, int layer);  /* offset of W_l in the padded vector */
 int pe_plan_bias_offset(const pe_plan *plan, int layer);
 int pe_plan_weight_ld(const pe_plan *plan, int layer);      /* padded row stride of W_l */
-/* does `engine` (PE_ENGINE_*) implement residual `kind` with K streams for this network?  The tensor-core engines
-   cover hidden widths <= 56: PE_ENGINE_TC_* the PE_RES_F5 term, PE_ENGINE_TCP_* / PE_ENGINE_TCS_* PE_RES_F5 and PE_RES_F7;
-   the SIMT engine covers everything. */
+/* does `engine` (PE_ENGINE_*) implement residual `kind` with K streams for this network?  The tensor-core engines cover the
+   PE_RES_F5 and PE_RES_F7 collocation terms of networks with hidden widths <= 56; the SIMT engine covers everything. */
 int pe_engine_supported(const pe_plan *plan, int kind, int K, int engine);
 /* number of CTAs (= gradient-partial slots) a launch over n points uses, and its scratch size in floats */
 int pe_plan_slots(const pe_plan *plan, int n_points, int K, int engine);
@@ -223,24 +215,10 @@ int pe_vec_axpy(int n, float *d_out, const float *d_x, float alpha, const float 
 int pe_vec_dot_max(int n, const float *d_a, const float *d_b, float *d_res, void *stream);
 
 /* ---------------------------------------------------------------- debug / profiling */
-/* Per-phase cycle counters of the tensor-core residual kernel: d_counters16 = 16 device uint64 (or NULL to switch off);
- * CTA 0 / thread 0 accumulates clock64 deltas per phase (tests/tc_phase_profile.py, profiles/r1_tc3_phase_cycles.txt). */
-void pe_debug_set_tc_profile(unsigned long long *d_counters16);
-/* Same for the PE_ENGINE_TCP_* kernels (selects their profiling instantiation while non-NULL). */
-void pe_debug_set_tcp_profile(unsigned long long *d_counters16);
-/* PE_ENGINE_TCF: same layout as pe_debug_set_tcs_profile. */
-void pe_debug_set_tcf_profile(unsigned long long *d_counters32);
-/* PE_ENGINE_TCS_*: d_counters32 = 32 device uint64: 0..15 phases of epilogue thread 0, 16..31 phases of the MMA/TMA issuer (CTA 0). */
-void pe_debug_set_tcs_profile(unsigned long long *d_counters32);
-/* EXPERIMENTAL (round-2 groundwork, csrc/pe_tc4_probe.cu; not used by any product path): forward jets d_out[n][K][O] like
- * pe_forward_jets, computed on tensor cores with the fp16-hi + bf16-lo operand split (mixed-format kind::f16 MMAs, one accumulator).
- * K = 4 or 5, hidden widths <= 56, <= 8 outputs.  d_scratch: pe_debug_tc4_scratch_bytes(plan) bytes.  variant bit 0: 1 = 7-chunk operand
- * planes with LBO = 0 on the last K-step, 0 = 8-chunk planes with a zero pad chunk. */
-size_t pe_debug_tc4_scratch_bytes(const pe_plan *plan);
-int pe_debug_forward_jets_tc4(const pe_plan *plan, int K, const float *d_points, int ld, int n, const float *in_scale, const float *in_shift,
-                              const float *d_params, void *d_scratch, float *d_out, int variant, void *stream);
-/* PE_ENGINE_TCP_*: 1 (default) = pipelined weight-gradient phase, 0 = the serial phase order of PE_ENGINE_TC_* (A/B timing). */
-void pe_debug_set_tcp_pipeline(int on);
+/* Per-phase cycle counters of the tensor-core residual kernels: d_counters32 = 32 device uint64 (or NULL to switch off): 0..15 phases of
+ * epilogue thread 0, 16..31 phases of the MMA/TMA issuer of CTA 0 (tests/tcf_gpu_check.py prof; selects the profiling instantiation). */
+void pe_debug_set_tcs_profile(unsigned long long *d_counters32);     /* PE_ENGINE_TCS_* */
+void pe_debug_set_tcf_profile(unsigned long long *d_counters32);     /* PE_ENGINE_TCF */
 
 #ifdef __cplusplus
 }

@@ -23,15 +23,13 @@ PE_TILE_POINTS = 32
 PE_TC_TILE = 128
 
 RES_F5, RES_F7, RES_COLS, RES_TRACTION, RES_DT = 0, 1, 2, 3, 4
-ENGINE_SIMT_FP32, ENGINE_TC_TF32X3, ENGINE_TC_TF32, ENGINE_TCP_TF32X3, ENGINE_TCP_TF32, ENGINE_TCS_TF32X3, ENGINE_TCS_TF32 = 0, 1, 2, 3, 4, 5, 6
-ENGINE_TCF = 8        # fp16-pair tcgen05 engine (csrc/pe_tcf.cu)
-ENGINE_TC4 = 7        # EXPERIMENTAL fourth generation (csrc/pe_tc4.cu): not validated on hardware yet, opt-in only
-# 'tc3p' / 'tc1p': second-generation tcgen05 engine (csrc/pe_tcp.cu: pipelined weight-gradient phase, F5 and F7)
-# 'tc3s' / 'tc1s': third generation (csrc/pe_tcs.cu: warp-specialised, stream groups pipelined through the forward pass)
-ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3': ENGINE_TC_TF32X3, 'tc1': ENGINE_TC_TF32, 'tc3p': ENGINE_TCP_TF32X3, 'tc1p': ENGINE_TCP_TF32,
-           'tc3s': ENGINE_TCS_TF32X3, 'tc1s': ENGINE_TCS_TF32,
-           'tc4': ENGINE_TC4, 'tcf': ENGINE_TCF,
-           'auto': ENGINE_TCS_TF32X3}      # fastest fp32-parity engine; terms it does not implement run on the SIMT engine (engine.py build())
+ENGINE_SIMT_FP32, ENGINE_TCS_TF32X3, ENGINE_TCS_TF32, ENGINE_TCF = 0, 5, 6, 8
+# 'tcf'  : fp16-pair tcgen05 engine (csrc/pe_tcf.cu): fp32-grade (measured <= 7e-7 on loss terms, <= 5e-6 on gradient blocks, <= 8.3e-6 on the
+#          reference's 20-step Adam curves: profiles/r2_refgold_report_tcf.jsonl) -- what 'auto' selects
+# 'tc3s' : TF32x3 tcgen05 engine (csrc/pe_tcs.cu), measured 5e-6 .. 8e-6 / 3.3e-5: A/B partner only;  'tc1s': its single-pass TF32 mode
+# 'simt' : fp32 FFMA engine, any width, every residual kind: the parity anchor
+ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3s': ENGINE_TCS_TF32X3, 'tc1s': ENGINE_TCS_TF32, 'tcf': ENGINE_TCF,
+           'auto': ENGINE_TCF}             # terms / networks the tensor-core engine does not implement run on the SIMT engine (engine.py build())
 
 
 class TermDesc(C.Structure):
@@ -82,13 +80,8 @@ SYMBOLS = [
     ('pe_lbfgs_store_pair', _i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ('pe_vec_axpy', _i, [_i, _vp, _vp, _f, _vp, _vp]),
     ('pe_vec_dot_max', _i, [_i, _vp, _vp, _vp, _vp]),
-    ('pe_debug_set_tc_profile', None, [_vp]),
-    ('pe_debug_set_tcp_profile', None, [_vp]),
-    ('pe_debug_set_tcp_pipeline', None, [_i]),
     ('pe_debug_set_tcs_profile', None, [_vp]),
     ('pe_debug_set_tcf_profile', None, [_vp]),
-    ('pe_debug_tc4_scratch_bytes', C.c_size_t, [_vp]),
-    ('pe_debug_forward_jets_tc4', _i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp, _i, _vp]),
 ]
 
 _lib = None

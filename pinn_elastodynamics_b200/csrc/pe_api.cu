@@ -15,21 +15,31 @@ void pe_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int pe_launch_resid_tc(const pe_plan* plan, const PeResidArgs& a, int K, int engine, int slots, cudaStream_t st,
-                       const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
-int pe_launch_resid_tcp(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
-                        const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 int pe_launch_resid_tcs(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
-                        const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
-int pe_launch_resid_tc4(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
-int pe_tc_supported(const pe_plan* plan, int K, int engine);
-int pe_tcp_supported(const pe_plan* plan, int K);
-int pe_tc_slots(const pe_plan* plan, int n_points);
-size_t pe_tc_stash_floats_per_slot(const pe_plan* plan);
-size_t pe_tc_image_floats(const pe_plan* plan);
+
+// ---- sizing shared by the tcgen05 engines: 128-point tiles, one persistent CTA per SM (= one gradient-partial slot each); per slot a stash
+// of (L-1) layers x 5 streams x 28,672 B (fp32 [chunk of 4][128][4] planes in pe_tcs.cu, fp16-pair planes in pe_tcf.cu: same bytes), then the
+// operand images of every matrix (the larger of the two engines' formats: 2 x 36,864 B per matrix)
+static const int TCG_STASH_LAYER_BYTES = 5 * 28672, TCG_IMG_LAYER_BYTES = 2 * 36864;
+int pe_tc_slots(const pe_plan* plan, int n_points) {      // for a fused launch pass 128 * (tiles of set 1 + tiles of set 2)
+    int ntiles = (n_points + PE_TC_TILE - 1) / PE_TC_TILE;
+    int s = ntiles < plan->sms ? ntiles : plan->sms;
+    return s < 1 ? 1 : s;
+}
+size_t pe_tc_stash_floats_per_slot(const pe_plan* plan) { return (size_t)(plan->lay.L - 1) * (TCG_STASH_LAYER_BYTES / 4) + 64; }
+size_t pe_tc_image_floats(const pe_plan* plan) { return (size_t)plan->lay.L * (TCG_IMG_LAYER_BYTES / 4); }
+// F5 (K = 5, 5 outputs) and F7 (K = 4, 7 outputs) collocation terms of networks with hidden widths <= 56 (7 chunks of 8 units per operand plane)
+static int tcgen_supported(const pe_plan* plan, int K) {
+    const PeLayout& lay = plan->lay;
+    const int O = lay.d[lay.L];
+    if (!((K == 5 && O == 5) || (K == 4 && O == 7)) || lay.L < 2) return 0;
+    for (int l = 1; l < lay.L; ++l)
+        if (lay.d[l] > 56) return 0;
+    return 1;
+}
 
 extern "C" int pe_version(void) { return 100; }
 extern "C" int pe_abi_sizeof_term_desc(void) { return (int)sizeof(pe_term_desc); }
@@ -112,17 +122,14 @@ extern "C" int pe_plan_bias_offset(const pe_plan* plan, int l) { return (plan &&
 extern "C" int pe_plan_weight_ld(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.ldw[l] : -1; }
 
 static bool is_tcs(int engine) { return engine == PE_ENGINE_TCS_TF32X3 || engine == PE_ENGINE_TCS_TF32; }
-static bool is_tc4(int engine) { return engine == PE_ENGINE_TC4; }
 static bool is_tcf(int engine) { return engine == PE_ENGINE_TCF; }
-static bool is_tcp(int engine) { return engine == PE_ENGINE_TCP_TF32X3 || engine == PE_ENGINE_TCP_TF32 || is_tcs(engine) || is_tc4(engine) || is_tcf(engine); }   // second generation onwards: F5 + F7
-static bool is_tc(int engine) { return engine == PE_ENGINE_TC_TF32X3 || engine == PE_ENGINE_TC_TF32 || is_tcp(engine); }
+static bool is_tc(int engine) { return is_tcs(engine) || is_tcf(engine); }
 
 extern "C" int pe_engine_supported(const pe_plan* plan, int kind, int K, int engine) {
     if (!plan) return 0;
     if (engine == PE_ENGINE_SIMT_FP32) return 1;
-    if ((is_tc4(engine) || is_tcf(engine)) && plan->lay.L < 3) return 0;
-    if (is_tcp(engine)) return (kind == PE_RES_F5 || kind == PE_RES_F7) && pe_tcp_supported(plan, K);
-    if (is_tc(engine)) return kind == PE_RES_F5 && pe_tc_supported(plan, K, engine);
+    if (is_tcf(engine) && plan->lay.L < 3) return 0;
+    if (is_tc(engine)) return (kind == PE_RES_F5 || kind == PE_RES_F7) && tcgen_supported(plan, K);
     return 0;
 }
 
@@ -229,7 +236,7 @@ static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K,
         return pe_launch_resid_simt(plan, a, K, pe_plan_slots(plan, n_local, K, engine), (cudaStream_t)stream);
     }
     if (is_tc(engine)) {
-        if (!pe_engine_supported(plan, term->kind, K, engine)) { pe_set_error("tensor-core engine %d does not support this residual kind / network (F5 K=5 [TCP: or F7 K=4], hidden widths <= 56)", engine); return 1; }
+        if (!pe_engine_supported(plan, term->kind, K, engine)) { pe_set_error("tensor-core engine %d does not support this residual kind / network (F5 K=5 or F7 K=4, hidden widths <= 56)", engine); return 1; }
         int n_eff = n_local;
         if (term2) {
             if (check_term(plan, term2, 1)) return 1;
@@ -239,13 +246,7 @@ static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K,
         }
         if (is_tcf(engine))
             return pe_launch_resid_tcf(plan, a, K, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
-        if (is_tc4(engine))
-            return pe_launch_resid_tc4(plan, a, K, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
-        if (is_tcs(engine))
-            return pe_launch_resid_tcs(plan, a, K, engine == PE_ENGINE_TCS_TF32 ? 1 : 0, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
-        if (is_tcp(engine))
-            return pe_launch_resid_tcp(plan, a, K, engine == PE_ENGINE_TCP_TF32 ? 1 : 0, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
-        return pe_launch_resid_tc(plan, a, K, engine, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
+        return pe_launch_resid_tcs(plan, a, K, engine == PE_ENGINE_TCS_TF32 ? 1 : 0, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
     }
     pe_set_error("unknown engine %d", engine);
     return 1;

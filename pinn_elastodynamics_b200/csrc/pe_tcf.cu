@@ -54,7 +54,7 @@ constexpr int F_IMG_LAYER = 2 * F_IMG;            // forward image, adjoint imag
 constexpr int F_ONES = 0;                                     // 1,024 B of fp16 ones: B operand of the bias-gradient MMAs
 constexpr int F_ACT = 1024;                                   // NS x (hi plane | lo plane)
 constexpr int F_R = F_ACT + TC_MAX_STREAMS * F_STREAM;        // 144,384: forward: two weight images; reverse: adjoint image + two staging buffers
-constexpr int F_STG = F_R + F_IMG;                            // staging buffer s at F_STG + s * F_STREAM
+constexpr int F_STG = F_R + F_IMG;                            // four staging slots of one plane each at F_STG + s * F_PLANE
 constexpr int F_MISC = F_R + F_IMG + 2 * F_STREAM;            // 218,112: mbarriers + TMEM base slot + tile scale
 constexpr int F_COORD = F_MISC + 256;
 constexpr int F_RED = F_COORD + 128 * 16;
@@ -63,7 +63,7 @@ constexpr int F_W0 = F_BIAS + PE_MAX_LAYERS * 256;            // [4][64] floats
 constexpr int F_TOTAL = F_W0 + 1024;                          // 229,632
 static_assert(2 * F_IMG <= F_IMG + 2 * F_STREAM, "the forward image double buffer lives inside the reverse-sweep region");
 static_assert(F_TOTAL <= 227 * 1024, "shared memory map exceeds the 227 KB opt-in limit");
-constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SEMPTY = 80, B_DW = 96, B_TMEM = 112, B_SCALE = 128;   // byte offsets in F_MISC
+constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SEMPTY = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144;   // byte offsets in F_MISC
 constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW: 56 hi-hi + 56 cross; bias: 8 + 8)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     }
     if (tid == 0) {
         for (int g = 0; g < 3; ++g) { mbar_init(bar_acc + 8 * g, 1); mbar_init(bar_act + 8 * g, F_EPI); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_img + 8 * b, 1); mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, 1); }
+        for (int b = 0; b < 2; ++b) mbar_init(bar_img + 8 * b, 1);
+        for (int b = 0; b < 4; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, 1); }
         mbar_init(bar_dw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -266,13 +267,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 for (int l = L; l >= 2; --l) {
                     const int dout = lay.d[l];
                     const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;     // outputs of layer l-1 = inputs A of layer l
-                    auto load_stage = [&](int k) {
-                        const uint32_t sb = (uint32_t)(k & 1);
-                        mbar_expect_tx(bar_sfull + 8 * sb, F_STREAM);
-                        tma_load_1d(stg_s + sb * F_STREAM, stash_in + (size_t)k * F_STREAM, F_STREAM, bar_sfull + 8 * sb);
+                    // the stashed planes of A_{l-1} come back one plane (hi or lo of one stream) per bulk copy into four staging slots:
+                    // item i = 2 k + (0: hi plane, 1: lo plane) of stream k lives in slot i & 3
+                    constexpr int NI = 2 * NS;
+                    auto load_item = [&](int i) {
+                        const uint32_t sl = (uint32_t)(i & 3);
+                        mbar_expect_tx(bar_sfull + 8 * sl, F_PLANE);
+                        tma_load_1d(stg_s + sl * F_PLANE, stash_in + (size_t)i * F_PLANE, F_PLANE, bar_sfull + 8 * sl);
                     };
-                    load_stage(0);                          // both staging buffers are free: the previous layer's DW phase is complete
-                    load_stage(1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) load_item(i);   // all four slots are free: the previous layer's DW phase is complete
+                    if (l > 2) {                                // pull the planes of the next (shallower) layer towards L2 while this layer runs
+                        const uint8_t* nxt = stash + (size_t)(l - 3) * STASH_LAYER;
+#pragma unroll
+                        for (int k = 0; k < NS; ++k)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + (size_t)k * F_STREAM), "r"(F_STREAM) : "memory");
+                    }
                     wait_img(0);
                     TCF_PROF(24);
                     wait_act(0); wait_act(1); wait_act(2);
@@ -289,33 +299,39 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
                     const uint32_t id112 = idesc_mn(112), id56 = idesc_mn(56), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
 #pragma unroll 1
-                    for (int k = 0; k < NS; ++k) {
-                        const uint32_t sb = (uint32_t)(k & 1);
-                        mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
-                        psfull ^= 1u << sb;
-                        const uint32_t a_hi = stg_s + sb * F_STREAM, a_lo = a_hi + F_PLANE;
+                    for (int i = 0; i < NI; ++i) {
+                        const uint32_t sl = (uint32_t)(i & 3);
+                        const int k = i >> 1;
+                        mbar_wait(bar_sfull + 8 * sl, (psfull >> sl) & 1u);
+                        psfull ^= 1u << sl;
+                        const uint32_t a_s = stg_s + sl * F_PLANE;
                         const uint32_t z_hi = act_s + (uint32_t)(k * F_STREAM), z_lo = z_hi + F_PLANE;
+                        if (!(i & 1)) {                                      // hi plane:  Ah^T [Zh | Zl]
 #pragma unroll 1
-                        for (int s = 0; s < 8; ++s) {
-                            const uint32_t o = (uint32_t)(s * 256);          // 16 points x 16 B
-                            const uint64_t dah = sdesc(a_hi + o, 128, F_CH), dal = sdesc(a_lo + o, 128, F_CH);
-                            const uint64_t dzh = sdesc(z_hi + o, 128, F_CH), dzl = sdesc(z_lo + o, 128, F_CH);
-                            const uint32_t first = (k > 0 || s > 0) ? 1u : 0u;
-                            if (nzc == 7) {                                  // [Zh | Zl] are contiguous: one N = 112 MMA
-                                mma_bf16_ss(tbase + T_DW, dah, dzh, id112, first);
-                                mma_bf16_ss(tbase + T_DW + 56, dal, dzh, id56, 1u);
-                            } else {
-                                mma_bf16_ss(tbase + T_DW, dah, dzh, idz, first);
-                                mma_bf16_ss(tbase + T_DW + 56, dah, dzl, idz, first);
-                                mma_bf16_ss(tbase + T_DW + 56, dal, dzh, idz, 1u);
+                            for (int s = 0; s < 8; ++s) {
+                                const uint32_t o = (uint32_t)(s * 256);      // 16 points x 16 B
+                                const uint64_t da = sdesc(a_s + o, 128, F_CH);
+                                const uint32_t first = (i > 0 || s > 0) ? 1u : 0u;
+                                if (nzc == 7) {                              // the two Z planes are contiguous: one N = 112 MMA
+                                    mma_bf16_ss(tbase + T_DW, da, sdesc(z_hi + o, 128, F_CH), id112, first);
+                                } else {
+                                    mma_bf16_ss(tbase + T_DW, da, sdesc(z_hi + o, 128, F_CH), idz, first);
+                                    mma_bf16_ss(tbase + T_DW + 56, da, sdesc(z_lo + o, 128, F_CH), idz, first);
+                                }
+                            }
+                        } else {                                             // lo plane:  Al^T Zh
+#pragma unroll 1
+                            for (int s = 0; s < 8; ++s) {
+                                const uint32_t o = (uint32_t)(s * 256);
+                                mma_bf16_ss(tbase + T_DW + 56, sdesc(a_s + o, 128, F_CH), sdesc(z_hi + o, 128, F_CH), nzc == 7 ? id56 : idz, 1u);
                             }
                         }
-                        if (k + 2 < NS) mma_commit(bar_sempty + 8 * sb);       // this buffer is refilled (stream k + 2) once its MMAs are complete
-                        if (k >= 1 && k + 1 < NS) {                          // ... which is waited for one stream later, behind the next stream's MMAs
-                            const uint32_t ob = sb ^ 1u;
+                        if (i + 4 < NI) mma_commit(bar_sempty + 8 * sl);       // this slot is refilled (item i + 4) once its MMAs are complete
+                        if (i >= 1 && i + 3 < NI) {                          // ... which is waited for one item later, behind the next item's MMAs
+                            const uint32_t ob = (uint32_t)((i - 1) & 3);
                             mbar_wait(bar_sempty + 8 * ob, (psempty >> ob) & 1u);
                             psempty ^= 1u << ob;
-                            load_stage(k + 1);
+                            load_item(i + 3);
                         }
                     }
                     {   // bias gradient: column 0 of  Zh^T 1  (and of  Zl^T 1): the value-stream plane is the MN-major A operand (M = 64 units;

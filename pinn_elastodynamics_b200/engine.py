@@ -186,6 +186,8 @@ class LossEngine:
         t = Term(name, kind, K, local, desc, aux)
         t.global_n = N
         t.global_lo = a
+        t.host = pts                          # global rows (host, fp32): source of chunk re-sharding (set_chunk, world > 1)
+        t.resident = local                    # this rank's shard of the whole set
         self.terms.append(t)
         self._built = False
         return t
@@ -194,12 +196,21 @@ class LossEngine:
         """Activate GLOBAL rows [g_lo, g_hi) of a term (reference `batch_num` chunking, semi:299-305).
         The mean is over the chunk's rows; each rank processes its part of the chunk."""
         if (g_lo, g_hi) == (0, term.global_n):          # whole set: this rank's resident shard
+            term.points = term.resident
             term.lo, term.hi = 0, term.points.shape[0]
             term.desc.n_global = term.global_n
-        else:
-            if self.world > 1:
-                raise L.PeError('batch_num chunking with world_size > 1 is not supported')
+        elif self.world == 1:
+            term.points = term.resident
             term.lo, term.hi = g_lo, g_hi
+            term.desc.n_global = g_hi - g_lo
+        else:
+            # every rank takes its index shard OF THE CHUNK (same arithmetic, semi:300-302), so a chunk is spread over all GPUs instead of
+            # living on the ranks whose resident shard happens to contain it; one H2D copy per chunk switch (once per `iter` steps)
+            if term.aux is not None:
+                raise L.PeError('batch_num chunking of a composite (aux) point set with world_size > 1 is not supported')
+            a, b = shard_range(g_hi - g_lo, self.rank, self.world)
+            term.points = torch.from_numpy(term.host[g_lo + a:g_lo + b]).to(self.device)
+            term.lo, term.hi = 0, b - a
             term.desc.n_global = g_hi - g_lo
         self._built = False
 
@@ -219,9 +230,11 @@ class LossEngine:
             if t.fused_into is not None:
                 t.slots, t.slot_base = 0, base
                 continue
-            n = max(t.hi - t.lo, 1)
+            # slot count = what the launch itself derives from the real row counts (csrc/pe_api.cu residual_common): an empty shard or
+            # chunk still runs one CTA that zero-fills its slot
+            n = t.hi - t.lo
             if t.fused is not None:
-                tiles = -(-n // L.PE_TC_TILE) + -(-max(t.fused.hi - t.fused.lo, 1) // L.PE_TC_TILE)
+                tiles = -(-n // L.PE_TC_TILE) + -(-(t.fused.hi - t.fused.lo) // L.PE_TC_TILE)
                 n = tiles * L.PE_TC_TILE
             t.slots = self.lib.pe_plan_slots(self.net.plan, n, t.K, t.engine)
             t.slot_base = base
@@ -250,7 +263,7 @@ class LossEngine:
                 continue
             n = t.hi - t.lo
             pts = t.points[t.lo:t.hi] if (t.lo, t.hi) != (0, t.points.shape[0]) else t.points
-            aux = None if t.aux is None else t.aux[t.lo:t.hi]
+            aux = None if t.aux is None else (t.aux[t.lo:t.hi] if n > 0 else t.aux)      # an empty slice has no data pointer
             if self.kernel_events is not None:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()

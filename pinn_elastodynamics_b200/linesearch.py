@@ -77,6 +77,8 @@ def strong_wolfe(phi, f0, dphi0, alpha, c1=1e-3, c2=0.9, maxls=20, budget=None):
     # exhausted: accept the best sufficient-decrease point seen, if any
     if a_lo > 0.0 and f_lo < f0:
         if last is None or last[0] != a_lo:
+            if budget is not None and budget() <= 0:                   # maxfun is a hard limit: no re-evaluation at a_lo, the caller restores x0
+                return False, 0.0, f0, dphi0, None
             fa, da, aux = phi(a_lo)
             return True, a_lo, fa, da, aux
         return True, last[0], last[1], last[2], last[3]

@@ -64,12 +64,11 @@ class _Base:
         self.uv_layers = list(uv_layers)
         self.verbose = verbose
         self.dtype = dtype
-        # engine: 'simt' (fp32 FFMA, any width: the parity anchor), 'auto' (= 'tc3s': tcgen05 engine for the collocation term where the
-        # net fits it -- hidden width <= 56, F5 / F7 -- and the SIMT engine for every other term), or an explicit name from
-        # _lib.ENGINES.  None reads $PE_ENGINE (default 'simt'), so a caller that keeps the reference's constructor signature can
-        # still pick the fast path.
+        # engine: 'auto' (the tcgen05 engine for the collocation term where the net fits it -- hidden width <= 56, F5 / F7 -- and the fp32
+        # SIMT engine for every other term and every other net), 'simt' (fp32 FFMA everywhere: the parity anchor), or an explicit name
+        # from _lib.ENGINES.  None (a caller that keeps the reference's constructor signature) reads $PE_ENGINE, default 'auto'.
         if engine is None:
-            engine = os.environ.get('PE_ENGINE', 'simt')
+            engine = os.environ.get('PE_ENGINE', 'auto')
         self._engine_name = engine
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.uv_net = Network(self.uv_layers, self.device)
@@ -126,18 +125,23 @@ class _Base:
         self.h2d_bytes_per_step = self.d2h_bytes_per_step = 0
         if refeed:
             # double-buffered device copies of every point set + a copy stream: the upload of step i+1 overlaps the
-            # kernels of step i; the loss terms of step i-1 are read back while step i runs (queue stays 1-2 steps deep)
+            # kernels of step i; the loss terms of step i-1 are read back while step i runs (queue stays 1-2 steps deep).
+            # The pinned host copies, the second device buffers, the stream and the events live as long as the point sets do
+            # (the reference keeps its feed_dict arrays for the life of the object as well): a train() call allocates nothing.
             terms = [t for t in eng.terms if t.enabled]
-            pinned = [t.points.cpu().pin_memory() for t in terms]
-            bufs = [(t.points, torch.empty_like(t.points)) for t in terms]
-            self.h2d_bytes_per_step = sum(h.numel() * 4 for h in pinned)
-            host_rows = torch.zeros((2, L.PE_MAX_TERMS), dtype=torch.float32).pin_memory()
+            key = tuple(t.points.data_ptr() for t in terms)
+            rc = getattr(self, '_refeed_cache', None)
+            if rc is None or rc['key'] != key:
+                rc = self._refeed_cache = dict(
+                    key=key, pinned=[t.points.cpu().pin_memory() for t in terms], bufs=[(t.points, torch.empty_like(t.points)) for t in terms],
+                    host_rows=torch.zeros((2, L.PE_MAX_TERMS), dtype=torch.float32).pin_memory(), copy_stream=torch.cuda.Stream(self.device),
+                    up_done=[torch.cuda.Event(), torch.cuda.Event()], used_done=[torch.cuda.Event(), torch.cuda.Event()],
+                    step_done=[torch.cuda.Event(), torch.cuda.Event()])
+            pinned, bufs, host_rows, copy_stream = rc['pinned'], rc['bufs'], rc['host_rows'], rc['copy_stream']
+            up_done, used_done, step_done = rc['up_done'], rc['used_done'], rc['step_done']   # upload into buffer b finished / kernels reading
+            self.h2d_bytes_per_step = sum(h.numel() * 4 for h in pinned)                      # buffer b finished / loss row copied to the host
             self.d2h_bytes_per_step = L.PE_MAX_TERMS * 4
-            copy_stream = torch.cuda.Stream(self.device)
             main = torch.cuda.current_stream(self.device)
-            up_done = [torch.cuda.Event(), torch.cuda.Event()]          # upload into buffer b finished
-            used_done = [torch.cuda.Event(), torch.cuda.Event()]        # kernels reading buffer b finished
-            step_done = [torch.cuda.Event(), torch.cuda.Event()]        # loss row of this parity copied to the host
 
             def upload(b):
                 copy_stream.wait_event(used_done[b])
@@ -280,6 +284,7 @@ class _Base:
                     message = 'ABNORMAL: NOT A DESCENT DIRECTION'
                     break
                 count = 0                                               # drop the history, restart from steepest descent
+                _, gg, gmax = scalars(g)                                # ... whose first trial step is 1 / ||g|| of the CURRENT gradient
                 continue
             xprev.copy_(x); gprev.copy_(g)
             alpha0 = 1.0 if count > 0 else min(1.0, 1.0 / max(np.sqrt(gg), 1e-30))   # L-BFGS-B: first step 1/||d||

@@ -161,8 +161,8 @@ def plate_point_sets(rng=None, scale=1.0):
     return dict(Collo=XYT_c, HOLE=HOLE, IC=IC, LF=LF, RT=RT, UP=UP, LW=LW, DIST=DIST, lb=lb, ub=ub)
 
 
-def semi_point_sets(MAX_T=16.0, rng=None, scale=1.0):
-    """The point sets of the half-space wave driver (semi:675-729)."""
+def semi_point_sets(MAX_T=16.0, rng=None, scale=1.0, shuffled=True):
+    """The point sets of the half-space wave driver (semi:675-729), row-shuffled like the driver does before training (semi:765)."""
     n = lambda k: max(int(k * scale), 8)
     lb, ub = np.array([-15, -15, 0.0]), np.array([15, 15, MAX_T])
     xc, yc, r = 0.0, 0.0, 2.0
@@ -176,7 +176,80 @@ def semi_point_sets(MAX_T=16.0, rng=None, scale=1.0):
     XYT_c = DelSrcPT(XYT_c, xc, yc, r)
     tt = np.concatenate((np.linspace(0, 6, 153), np.linspace(6, MAX_T, 63)))[1:]
     SRC = source_ring(xc, yc, r, 150, tt, ricker)
+    if shuffled:
+        shuffle(XYT_c, SRC, IC, UP, rng=rng)
     return dict(Collo=XYT_c, SRC=SRC, IC=IC, UP=UP, lb=lb, ub=ub)
+
+
+def inf_point_sets(MAX_T=20.0, rng=None, scale=1.0, shuffled=True):
+    """The point sets of the infinite-domain wave driver (inf:641-705): IC on a 101 x 101 grid, UP 150 x 201 (built, unused by the loss),
+    120 k + 10 k LHS collocation points minus the source disc, Ricker source on 200 circle points x 352 times; row-shuffled like the
+    driver does before training (inf:732)."""
+    n = lambda k: max(int(k * scale), 8)
+    lb, ub = np.array([0.0, 0.0, 0.0]), np.array([30, 30, MAX_T])
+    xc, yc, r = 15.0, 15.0, 2.0
+    IC = np.concatenate(CartGrid(xmin=0, xmax=30, ymin=0, ymax=30, tmin=0, tmax=0, num=101, num_t=1), 1)
+    x_up, t_up = np.meshgrid(np.linspace(0, 30, 150), np.linspace(0, MAX_T, 201))
+    x_up, t_up = x_up.flatten()[:, None], t_up.flatten()[:, None]
+    UP = np.concatenate((x_up, np.full((x_up.size, 1), 30.0), t_up), 1)
+    XYT_c = lb + (ub - lb) * lhs(3, n(120000), rng)
+    XYT_c_ext = np.array([xc - r - 1, yc - r - 1, 0.0]) + np.array([2 * (r + 1), 2 * (r + 1), MAX_T]) * lhs(3, n(10000), rng)
+    XYT_c = DelSrcPT(np.concatenate((XYT_c, XYT_c_ext), axis=0), xc, yc, r)
+    tt = np.linspace(0, MAX_T, 353)[1:]
+    SRC = source_ring(xc, yc, r, 200, tt, ricker)
+    if shuffled:
+        shuffle(XYT_c, SRC, IC, UP, rng=rng)
+    return dict(Collo=XYT_c, SRC=SRC, IC=IC, UP=UP, lb=lb, ub=ub)
+
+
+def conf_point_sets(MAX_T=14.0, rng=None, scale=1.0):
+    """The point sets of the confined-wave driver (conf:883-968): DIST targets (built, unused by its net_uv), 6 k LHS IC points minus the
+    source disc, four fixed edges of 7 k points each, 120 k + 15 k + an edge band of a 50 k LHS set as collocation points, Gauss-pulse
+    source on 200 circle points x 281 times."""
+    n = lambda k: max(int(k * scale), 8)
+    lb, ub = np.array([-15.0, -15.0, 0.0]), np.array([15.0, 15.0, MAX_T])
+    xc, yc, r = 0.0, 0.0, 2.0
+    x_d, y_d, t_d = GenDistPt(xmin=-15.0, xmax=15.0, ymin=-15.0, ymax=15.0, tmin=0, tmax=MAX_T, xc=0.0, yc=0.0, r=2.0, num_surf_pt=120, num=21, num_t=21,
+                              arc=2 * np.pi)
+    DIST = GenDist_confined(np.concatenate((x_d, y_d, t_d), 1))
+    IC = DelSrcPT(lb + np.array([30.0, 30.0, 0.0]) * lhs(3, n(6000), rng), 0, 0, 2.0, strict=True)
+    LW = np.array([-15.0, -15.0, 0.0]) + np.array([30.0, 0.0, MAX_T]) * lhs(3, n(7000), rng)
+    UP = np.array([-15.0, 15.0, 0.0]) + np.array([30.0, 0.0, MAX_T]) * lhs(3, n(7000), rng)
+    LF = np.array([-15.0, -15.0, 0.0]) + np.array([0.0, 30.0, MAX_T]) * lhs(3, n(7000), rng)
+    RT = np.array([15.0, -15.0, 0.0]) + np.array([0.0, 30.0, MAX_T]) * lhs(3, n(7000), rng)
+    FIXED = np.concatenate((LF, RT, LW, UP), 0)
+    XYT_c = lb + (ub - lb) * lhs(3, n(120000), rng)
+    XYT_c_ext = np.array([xc - r - 1, yc - r - 1, 0.0]) + np.array([2 * (r + 1), 2 * (r + 1), MAX_T]) * lhs(3, n(15000), rng)
+    XYT_c_ext2 = lb + (ub - lb) * lhs(3, n(50000), rng)
+    XYT_c_ext2 = XYT_c_ext2[(np.abs(XYT_c_ext2[:, 0]) > 12) | (np.abs(XYT_c_ext2[:, 1]) > 12), :]
+    XYT_c = DelSrcPT(np.concatenate((XYT_c, XYT_c_ext, XYT_c_ext2), axis=0), xc, yc, r, strict=True)
+    tt = np.concatenate((np.linspace(0, 4, 141), np.linspace(4, MAX_T, 141)), 0)[1:]
+    SRC = source_ring(xc, yc, r, 200, tt, gauss_pulse)
+    return dict(Collo=XYT_c, SRC=SRC, IC=IC, FIXED=FIXED, DIST=DIST, lb=lb, ub=ub)
+
+
+def time_march(make_model, point_sets, horizons, train, checkpoint=None):
+    """The drivers' curriculum ("Need pretraining!! (i.e. train for 10s -> 15s -> 25s)", inf:636-638; "train 7s -> 14s", conf:884;
+    semi:670-672): train on [0, T_1], save, rebuild the point sets for the longer horizon T_2, warm-start from the saved weights, ...
+    The reference does this by editing MAX_T and the pickle name by hand between runs; here it is one loop.
+
+    make_model(sets, warm_start_path_or_None) -> model;  point_sets(MAX_T) -> dict (e.g. semi_point_sets);
+    train(model, MAX_T) runs the stage's optimiser calls;  checkpoint(MAX_T) -> path of the pickle written after the stage
+    (default: a temporary file per stage).  Returns the last model and the list of (MAX_T, path)."""
+    import os
+    import tempfile
+    saved, model, path = [], None, None
+    tmp = tempfile.mkdtemp(prefix='pe_march_') if checkpoint is None else None
+    for T in horizons:
+        model = make_model(point_sets(T), path)
+        train(model, T)
+        path = checkpoint(T) if checkpoint is not None else os.path.join(tmp, 'uv_NN_%gs.pickle' % T)
+        try:
+            model.save_NN(path)
+        except TypeError:                      # PINN / DeepElasticWave: save_NN(fileDir, TYPE)
+            model.save_NN(path, 'UV')
+        saved.append((T, path))
+    return model, saved
 
 
 # ----------------------------------------------------------------------------- FEM ground truth + metrics

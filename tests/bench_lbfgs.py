@@ -9,7 +9,7 @@ import bench
 from oracle import ref_torch as R
 import pinn_elastodynamics_b200 as pe
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
-eng = sys.argv[2] if len(sys.argv) > 2 else 'tc3'
+eng = sys.argv[2] if len(sys.argv) > 2 else 'tcf'
 EV = int(sys.argv[3]) if len(sys.argv) > 3 else 300
 Collo, HOLE = bench.make_workload(N)
 layers = [3] + 5 * [50] + [5]

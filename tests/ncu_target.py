@@ -1,5 +1,5 @@
 """Run on the GPU box under ncu: a few Adam steps of the bench workload (BASELINE config 2: 50,000 collocation + 5,000 hole
-points, 5x50 net) on one engine, nothing else in the process.     python tests/ncu_target.py [engine=tc3s] [steps=6]"""
+points, 5x50 net) on one engine, nothing else in the process.     python tests/ncu_target.py [engine=tcf] [steps=6]"""
 import os
 import sys
 
@@ -11,7 +11,7 @@ import bench                                    # noqa: E402  (make_workload onl
 from oracle import ref_torch as R               # noqa: E402  (Xavier arrays only)
 import pinn_elastodynamics_b200 as pe           # noqa: E402
 
-engine = sys.argv[1] if len(sys.argv) > 1 else 'tc3s'
+engine = sys.argv[1] if len(sys.argv) > 1 else 'tcf'
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 layers = [3] + 5 * [50] + [5]
 Collo, HOLE = bench.make_workload(50000)

@@ -51,7 +51,7 @@ def _run(world, engine, tmp_path, peer=True):
     return json.loads(line[0][7:])
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3', 'tc3s'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf', 'tc3s'])
 def test_two_gpus_match_one(engine, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -68,6 +68,6 @@ def test_peer_memory_allreduce_equals_nccl_path(tmp_path):
     with 2 ranks both add the two partial sums once (a + b), so the trajectories agree bit for bit."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    a, b = _run(2, 'tc3s', tmp_path, peer=True), _run(2, 'tc3s', tmp_path, peer=False)
+    a, b = _run(2, 'tcf', tmp_path, peer=True), _run(2, 'tcf', tmp_path, peer=False)
     assert a['peer'] and not b['peer']
     assert a['terms'] == b['terms'] and a['g'] == b['g'] and a['curve'] == b['curve'] and a['params'] == b['params']

@@ -69,13 +69,13 @@ def _plate(pe, Collo, HOLE, layers, Ws, bs, engine='simt'):
     return m
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_gpu_driver_reaches_scipy_loss(pe, golden, engine):
     """Same objective, same options: after the same evaluation budget the device-resident driver must be at least as low as
     1.5x the loss SciPy's L-BFGS-B reaches (different line search => different iterates; both monotone), and the loss it
     reports must equal a fresh evaluation at the parameters it leaves in the network."""
     g = golden('synthetic_5x50.npz')
-    layers = [3, 50, 50, 50, 50, 50, 5] if engine == 'tc3' else [3, 20, 20, 5]
+    layers = [3, 50, 50, 50, 50, 50, 5] if engine == 'tcf' else [3, 20, 20, 5]
     Ws, bs = R.xavier_params(layers, seed=21)
     Collo, HOLE = g['f5_collo'][:2000], g['f5_hole'][:200]
     opts = dict(maxiter=150, maxfun=150, maxcor=50, maxls=50, ftol=1e-5 * np.finfo(float).eps)
@@ -111,7 +111,7 @@ def test_gpu_driver_limits_and_pretraining(pe, golden):
     assert r.fun < f0
 
 
-@pytest.mark.parametrize('engine,layers', [('simt', [3, 18, 22, 5]), ('simt', [3, 20, 20, 5]), ('tc3', [3, 50, 50, 50, 50, 50, 5])])
+@pytest.mark.parametrize('engine,layers', [('simt', [3, 18, 22, 5]), ('simt', [3, 20, 20, 5]), ('tcf', [3, 50, 50, 50, 50, 50, 5])])
 def test_gradient_pads_are_zero(pe, golden, engine, layers):
     """The device-resident optimiser takes dot products over the PADDED parameter vector, so the pad entries of the reduced
     gradient (row strides rounded to 4, slack between matrices) must be exactly zero and stay zero through Adam steps."""

@@ -49,7 +49,7 @@ def _check(m, T_ref, names, g_ref, layers, tol_t, tol_g):
     return t, g
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_f5_plain_5x50_random_init(pe, golden, engine):
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
@@ -62,7 +62,7 @@ def test_f5_plain_5x50_random_init(pe, golden, engine):
     _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 1e-5, 2e-5)
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_f5_golden_terms_and_grad(pe, golden, engine):
     """zero-bias Xavier init exactly as stored in the golden file"""
     g = golden('synthetic_5x50.npz')
@@ -187,7 +187,7 @@ def test_ragged_and_large_point_counts(pe, n):
     _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 2e-5, 5e-5)
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_bitwise_deterministic(pe, golden, engine):
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
@@ -200,7 +200,7 @@ def test_bitwise_deterministic(pe, golden, engine):
     assert np.array_equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_adam_curve_matches_golden(pe, golden, engine):
     """20 Adam steps, post-update losses (plate:496-506) vs the float64 oracle curve."""
     g = golden('synthetic_5x50.npz')
@@ -209,10 +209,8 @@ def test_adam_curve_matches_golden(pe, golden, engine):
     m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine=engine)
     l_uv, l_s, l_h, loss = m.train(20, 5e-4)
     C = g['f5_curve']
-    # SIMT fp32: 1e-5 on every term.  tcgen05 engine: the weighted total loss (the curve BASELINE names) to 1e-5; its
-    # smallest term (loss_f_uv ~ 2e-3 next to loss_f_s ~ 9) to 3e-5 -- the tensor-core accumulator truncates (not rounds)
-    # each of the 18 partial-sum updates per output, a ~2^-18 systematic bias per layer that the FFMA path does not have.
-    tol = 1e-5 if engine == 'simt' else 3e-5
+    # 1e-5 on every term and on the weighted total (the curve BASELINE names), SIMT and fp16-pair tcgen05 engine alike
+    tol = 1e-5
     np.testing.assert_allclose(l_uv, C[:, 0], rtol=tol)
     np.testing.assert_allclose(l_s, C[:, 1], rtol=tol)
     np.testing.assert_allclose(l_h, C[:, 2], rtol=tol)
@@ -306,12 +304,12 @@ def test_tc_ragged_and_large_point_counts(pe, n):
     HOLE = rng.uniform([0, 0, 0], [.1, .1, 10], (max(1, n // 7), 3))
     orc = R.Oracle('plate', Ws, bs)
     T, loss, gref = orc.loss_and_grad({'Collo': Collo, 'HOLE': HOLE})
-    m = _plate(pe, Collo, HOLE, layers, Ws, bs, engine='tc3')
+    m = _plate(pe, Collo, HOLE, layers, Ws, bs, engine='tcf')
     _check(m, T, ('loss_f_uv', 'loss_f_s', 'loss_HOLE'), gref, layers, 2e-5, 5e-5)
-    assert m.engine.terms[0].engine == 1, 'tensor-core engine was not selected for the collocation term'
+    assert m.engine.terms[0].engine == 8, 'tensor-core engine was not selected for the collocation term'
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_f5_composite_5x50(pe, golden, engine):
     """hard-BC composite u = P + D*N (plate:382-387) with the shipped dist/part nets around a 5x50 uv net"""
     g = golden('plate_ckpt.npz')
@@ -327,11 +325,11 @@ def test_f5_composite_5x50(pe, golden, engine):
 
 
 def test_tc_fast_mode_is_tf32_accurate(pe, golden):
-    """PE_ENGINE_TC_TF32 (single-pass TF32, no split): ~1e-3 class, stated separately from the fp32-parity engines"""
+    """PE_ENGINE_TCS_TF32 (single-pass TF32, no split): ~1e-3 class, stated separately from the fp32-parity engines"""
     g = golden('synthetic_5x50.npz')
     layers = [3] + 5 * [50] + [5]
     Ws, bs = R.xavier_params(layers, seed=1111)
-    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine='tc1')
+    m = _plate(pe, g['f5_collo'], g['f5_hole'], layers, Ws, bs, engine='tc1s')
     m.engine.evaluate()
     t = m.engine.terms_host()
     np.testing.assert_allclose(t[:2], g["f5_terms"][:2], rtol=3e-2)
@@ -390,7 +388,7 @@ def test_plate_pretraining_losses_and_lbfgs(pe, golden):
     assert 'loss_PART' in vals and 'loss_DIST' in vals
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_refeed_path_equals_resident_path(pe, golden, engine):
     """train(refeed=True) (bench `e2e`: per-step host->device re-upload, pipelined through two device buffers, loss read back
     every step) must produce exactly the same trajectory as the resident path."""
@@ -404,7 +402,7 @@ def test_refeed_path_equals_resident_path(pe, golden, engine):
 
 
 # ------------------------------------------------------------------------------ BASELINE full sizes
-@pytest.mark.parametrize('engine', ['simt', 'tc3'])
+@pytest.mark.parametrize('engine', ['simt', 'tcf'])
 def test_full_size_50k_parity_and_shard_additivity(pe, engine):
     """BASELINE config 2 size (50,000 collocation + 5,000 hole points, 5x50 net): CUDA vs the float64 oracle on the full set,
     and the size-independent property the multi-GPU path relies on: per-shard sums / N_global add up to the whole-set result."""
@@ -440,7 +438,7 @@ def test_plate_recipe_end_to_end(pe, golden):
     S = P.plate_point_sets(rng=np.random.default_rng(11), scale=0.01)
     uv, dl, pl = [3, 30, 30, 30, 5], [3, 10, 10, 5], [3, 10, 10, 5]
     m = pe.PINN(S['Collo'], S['HOLE'][::10], S['IC'], S['LF'], S['RT'], S['UP'], S['LW'], S['DIST'][::5], uv, dl, pl, S['lb'], S['ub'],
-                verbose=False, engine='tc3')
+                verbose=False, engine='tcf')
     opts = dict(maxiter=40, maxfun=60, maxcor=50, maxls=50, ftol=1e-5 * np.finfo(float).eps)
     m.train_bfgs_dist(opts); m.train_bfgs_part(opts)
     v0 = m.getloss()

@@ -3,9 +3,10 @@ produced by the reference's own class files (tests/golden/reference_tf1shim.npz;
 tests/test_reference_golden.py for how they were made and how the oracle is pinned to them).
 
 fp32 tolerances (the reference computes plate / semi / conf in float64, inf in float32):
-  loss terms 1e-5 (2e-5 composite), gradient <= 2e-5 of each W_l / b_l block's max (3e-5 wave nets on tensor cores, 5e-5 composite),
-  Adam loss curves: SIMT engine 1e-5 everywhere; tensor-core engine 3e-5 on well-behaved trajectories, 1e-4 on the deliberately violent plate
-  trajectory (see the comment there);
+  loss terms 1e-5 (2e-5 composite), gradient <= 2e-5 of each W_l / b_l block's max (3e-5 wave nets, 5e-5 composite),
+  Adam loss curves (the weighted total = the curve north_star names): 1e-5 on BOTH engines (measured: SIMT <= 7.5e-6, fp16-pair tcgen05 engine
+  <= 8.3e-6, profiles/r2_refgold_report_tcf.jsonl); per-term curves 1e-5, except the smallest term of the deliberately violent plate trajectory
+  on the tcgen05 engine (3e-5; see the comment there);
   predicted fields 2e-5 of the field's max.
 """
 import numpy as np
@@ -15,7 +16,7 @@ import torch
 from tests.util import layers_of, per_layer_grad_err, rel_err, unpack_golden
 
 pytestmark = pytest.mark.gpu
-ENGINES = ['simt', 'tc3s']
+ENGINES = ['simt', 'tcf']
 
 
 @pytest.fixture(scope='module')
@@ -71,13 +72,14 @@ def test_plate_plain_against_reference_source(pe, G, engine):
     # PINN.train(iter, learning_rate) -> (loss_f_uv[], loss_f_s[], loss_HOLE[], loss[]), recorded after each update (plate:475-506)
     out = m.train(20, 5e-4)
     C = G['plate_plain_adam']
-    # This trajectory is violent on purpose (loss 73 -> 1.5 -> 4 within 20 steps at lr 5e-4).  The SIMT engine (3e-7 per evaluation) follows
-    # the reference to 1e-5 throughout; the tensor-core engine (7e-6 per evaluation: TF32 split + truncating accumulation) was measured
-    # 2e-5 off after the first step and 3.3e-5 off at the step-14 minimum of the loss (profiles/r1_refgold_report.jsonl): its bar here is 1e-4.
-    tol = 1e-5 if engine == 'simt' else 1e-4
-    for i in range(4):
-        np.testing.assert_allclose(out[i], C[:, i], rtol=tol)
-    assert rel_err(m.uv_net.get_flat(), G['plate_plain_params_after_adam']) <= 1e-5      # measured 3e-7 (simt), 7e-7 (tc3s): profiles/r1_refgold_report.jsonl
+    # This trajectory is violent on purpose (loss 73 -> 1.5 -> 4 within 20 steps at lr 5e-4): it amplifies a per-evaluation error about
+    # tenfold.  The weighted total -- the loss curve north_star asks to match to 1e-5 -- is held to 1e-5 on both engines (measured 7.5e-6 SIMT,
+    # 8.2e-6 tcgen05).  Per term: SIMT 1e-5; tcgen05 1e-5 on loss_f_uv / loss_f_s and 3e-5 on loss_HOLE, the smallest term (0.3 % of the
+    # total), measured 1.9e-5 at the step-14 minimum (profiles/r2_refgold_report_tcf.jsonl).
+    np.testing.assert_allclose(out[3], C[:, 3], rtol=1e-5)
+    for i in range(3):
+        np.testing.assert_allclose(out[i], C[:, i], rtol=3e-5 if (engine != 'simt' and i == 2) else 1e-5)
+    assert rel_err(m.uv_net.get_flat(), G['plate_plain_params_after_adam']) <= 1e-5      # measured 3e-7 (simt), 4e-7 (tcf)
 
 
 @pytest.mark.parametrize('engine', ENGINES)
@@ -100,7 +102,7 @@ def test_plate_composite_against_reference_source(pe, G, engine):
         assert m.part_engine.terms_host()[0] == pytest.approx(ref[4], rel=1e-5)
         assert m.dist_engine.terms_host()[0] == pytest.approx(ref[5], rel=1e-5)
     out = m.train(8, 5e-4)
-    np.testing.assert_allclose(out[3], G['plate_comp_adam'][:, 3], rtol=3e-5)
+    np.testing.assert_allclose(out[3], G['plate_comp_adam'][:, 3], rtol=1e-5)
 
 
 @pytest.mark.parametrize('engine', ENGINES)
@@ -127,5 +129,5 @@ def test_waves_against_reference_source(pe, G, kind, engine):
     # train(iter, learning_rate, batch_num = 2): the reference's chunked Adam loop (semi:289-326); the weighted total is the last column
     out = m.train(6, 1e-3, 2)
     C = G[f'{kind}_adam_b2']
-    np.testing.assert_allclose(out[-1], C[:, -1], rtol=2e-3 if kind == 'inf' else 3e-5)
-    np.testing.assert_allclose(out[0], C[:, 0], rtol=2e-3 if kind == 'inf' else 1e-4)
+    np.testing.assert_allclose(out[-1], C[:, -1], rtol=2e-3 if kind == 'inf' else 1e-5)      # inf: the reference script itself runs in float32
+    np.testing.assert_allclose(out[0], C[:, 0], rtol=2e-3 if kind == 'inf' else 1e-5)

@@ -114,8 +114,8 @@ def test_models_require_cuda():
 
 
 def test_engine_support_matrix():
-    """which residual kinds / networks each engine takes (pe_engine_supported): the SIMT engine everything; the round-1 tcgen05
-    engine the F5 term with hidden widths <= 56; the pipelined tcgen05 engine F5 (K=5, 5 outputs) and F7 (K=4, 7 outputs)."""
+    """which residual kinds / networks each engine takes (pe_engine_supported): the SIMT engine everything; the tcgen05 engines the F5 (K = 5,
+    5 outputs) and F7 (K = 4, 7 outputs) collocation terms of networks with hidden widths <= 56 (the fp16-pair engine: >= 2 hidden layers)."""
     L, lib = _lib()
 
     def sup(layers, kind, K, engine):
@@ -126,26 +126,21 @@ def test_engine_support_matrix():
         lib.pe_plan_destroy(plan)
         return r
     f5, f7, w100 = [3] + 5 * [50] + [5], [3] + 5 * [50] + [7], [3] + 8 * [100] + [7]
-    for eng in ('simt', 'tc3', 'tc1', 'tc3p', 'tc1p', 'tc3s', 'tc1s'):
-        assert sup(f5, L.RES_F5, 5, eng) == 1
+    assert set(L.ENGINES) == {'simt', 'tc3s', 'tc1s', 'tcf', 'auto'} and L.ENGINES['auto'] == L.ENGINES['tcf']
+    for eng in ('simt', 'tc3s', 'tc1s', 'tcf', 'auto'):
+        assert sup(f5, L.RES_F5, 5, eng) == 1 and sup(f7, L.RES_F7, 4, eng) == 1
         assert sup(f5, L.RES_TRACTION, 1, eng) == (1 if eng == 'simt' else 0)      # data terms stay on the SIMT engine
         assert sup(f7, L.RES_COLS, 1, eng) == (1 if eng == 'simt' else 0)
-    assert sup(f7, L.RES_F7, 4, 'simt') == 1
-    assert sup(f7, L.RES_F7, 4, 'tc3') == 0 and sup(f7, L.RES_F7, 4, 'tc3p') == 1 and sup(f7, L.RES_F7, 4, 'tc1p') == 1
-    assert sup(f7, L.RES_F7, 4, 'tc3s') == 1 and sup(w100, L.RES_F7, 4, 'tc3s') == 0
-    assert sup(w100, L.RES_F7, 4, 'tc3p') == 0                                      # hidden width > 56: SIMT only
-    assert sup([3, 56, 56, 5], L.RES_F5, 5, 'tc3p') == 1 and sup([3, 57, 56, 5], L.RES_F5, 5, 'tc3p') == 0
-    assert sup([3, 50, 5], L.RES_F5, 5, 'tc3p') == 1                                # one hidden layer: FFMA first layer + tensor-core output layer
-    assert sup(f5, L.RES_F7, 4, 'tc3p') == 0 and sup(f7, L.RES_F5, 5, 'tc3p') == 0   # K / output count must match the formulation
-    # 'auto' is the validated warp-specialised engine; the experimental fourth generation is opt-in and needs two hidden layers
-    assert L.ENGINES['auto'] == L.ENGINES['tc3s'] != L.ENGINES['tc4']
-    assert sup(f5, L.RES_F5, 5, 'tc4') == 1 and sup(f7, L.RES_F7, 4, 'tc4') == 1 and sup([3, 50, 5], L.RES_F5, 5, 'tc4') == 0
-    assert sup(f5, L.RES_TRACTION, 1, 'tc4') == 0 and sup(w100, L.RES_F7, 4, 'tc4') == 0
+        assert sup(w100, L.RES_F7, 4, eng) == (1 if eng == 'simt' else 0)          # hidden width > 56: SIMT only
+        assert sup(f5, L.RES_F7, 4, eng) == sup(f7, L.RES_F5, 5, eng)              # K / output count must match the formulation (0 on tensor cores)
+    assert sup([3, 56, 56, 5], L.RES_F5, 5, 'tcf') == 1 and sup([3, 57, 56, 5], L.RES_F5, 5, 'tcf') == 0
+    assert sup([3, 50, 5], L.RES_F5, 5, 'tc3s') == 1 and sup([3, 50, 5], L.RES_F5, 5, 'tcf') == 0      # one hidden layer
     # slots / scratch queries are engine-aware
     dims = (C.c_int * len(f5))(*f5)
     plan = lib.pe_plan_create(dims, len(f5), -1)
-    assert lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3p']) == lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3']) == 148
-    assert lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3p']) == lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3'])
+    assert lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tcf']) == lib.pe_plan_slots(plan, 50000, 5, L.ENGINES['tc3s']) == 148
+    assert lib.pe_plan_slots(plan, 0, 5, L.ENGINES['tcf']) == 1 == lib.pe_plan_slots(plan, 0, 5, L.ENGINES['simt'])      # an empty shard still owns one (zero-filled) slot
+    assert lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tcf']) == lib.pe_plan_scratch_floats(plan, 50000, 5, L.ENGINES['tc3s'])
     lib.pe_plan_destroy(plan)
 
 

@@ -86,3 +86,42 @@ def test_helpers_match_the_reference_functions(golden):
     XYT = cat(P.GenDistPt(xmin=-15, xmax=15, ymin=-15, ymax=15, tmin=0, tmax=14, xc=0, yc=0, r=2.0, num_surf_pt=13, num=8, num_t=4, arc=2 * np.pi))
     np.testing.assert_array_equal(XYT, G['h_conf_GenDistPt'])
     np.testing.assert_allclose(P.GenDist_confined(XYT), G['h_conf_GenDist'], rtol=1e-15, atol=0)
+
+
+def test_default_point_sets_equal_the_reference_drivers(golden):
+    """plate / semi / inf / conf_point_sets() against fingerprints of the arrays the reference's own `__main__` bodies build (executed in
+    place from /root/reference by tests/golden/make_driver_point_sets.py; plate:871-929, semi:667-765, inf:634-732, conf:881-968), with
+    the numpy global stream seeded like the scripts (np.random.seed(1111), plate:22).  Equal means byte-equal float64 arrays."""
+    import hashlib
+    G = golden('driver_point_sets.npz')
+    for kind, build in (('plate', P.plate_point_sets), ('semi', P.semi_point_sets), ('inf', P.inf_point_sets), ('conf', P.conf_point_sets)):
+        np.random.seed(1111)
+        sets = build()
+        names = [k[len(kind) + 1:-6] for k in G.files if k.startswith(kind + '_') and k.endswith('_shape')]
+        assert names
+        for name in names:
+            a = np.ascontiguousarray(np.asarray(sets[name], np.float64))
+            assert tuple(G[f'{kind}_{name}_shape']) == a.shape, (kind, name, a.shape)
+            np.testing.assert_allclose([a.sum(), (a * a).sum()], G[f'{kind}_{name}_sums'], rtol=1e-12, err_msg=f'{kind} {name}')
+            assert np.array_equal(np.frombuffer(hashlib.sha256(a.tobytes()).digest(), np.uint8), G[f'{kind}_{name}_sha256']), (kind, name)
+
+
+def test_time_march_warm_starts_each_stage(tmp_path):
+    """the drivers' hand-edited curriculum (semi:670-672, inf:636-638, conf:884) as one loop: every stage is built on the longer horizon's
+    point sets and warm-started from the previous stage's pickle"""
+    calls = []
+
+    class Model:
+        def __init__(self, sets, warm):
+            self.sets, self.warm, self.w = sets, warm, (0 if warm is None else open(warm).read())
+
+        def save_NN(self, path):
+            open(path, 'w').write(str(int(self.w) + 1))
+
+    def train(m, T):
+        calls.append((T, m.sets['T'], m.warm))
+
+    model, saved = P.time_march(lambda s, w: Model(s, w), lambda T: dict(T=T), [7.0, 14.0, 20.0], train, checkpoint=lambda T: str(tmp_path / f'uv_{T:g}.pickle'))
+    assert [c[0] for c in calls] == [7.0, 14.0, 20.0] and [c[1] for c in calls] == [7.0, 14.0, 20.0]
+    assert calls[0][2] is None and calls[1][2] == saved[0][1] and calls[2][2] == saved[1][1]
+    assert open(saved[-1][1]).read() == '3' and model.sets['T'] == 20.0
