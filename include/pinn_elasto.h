@@ -56,6 +56,10 @@ enum {
                                   PE_RES_F7 (K = 4), hidden widths <= 56.  Measured 5e-6 .. 8e-6 against the reference goldens: kept as the A/B
                                   partner of PE_ENGINE_TCF, not selected by 'auto' */
     PE_ENGINE_TCS_TF32 = 6,    /* same, single-pass TF32 (1e-3 class) */
+    PE_ENGINE_TCF_F16FWD = 9,  /* PE_ENGINE_TCF with the FORWARD layer GEMMs as single fp16 products (11-bit significands, fp32 accumulation): the
+                                  "16-bit forward / fp32 gradient" mode of BASELINE config 3.  (The config names bf16; mixed-format MMAs are illegal on
+                                  B200 and the gradient GEMMs need the fp16 pair planes anyway, so the forward uses their hi halves: fp16, which is
+                                  at least as precise as bf16.)  Adjoint and weight-gradient GEMMs stay fp32-grade.  ~1e-3 class on the loss. */
     PE_ENGINE_TCF = 8,         /* fp16-pair tcgen05 engine (csrc/pe_tcf.cu): every GEMM operand as an fp16 pair (hi, lo scaled by 2^11), products
                                   Ah Bh + 2^-11 (Ah Bl + Al Bh) on kind::f16 MMAs with the scale-input-d form, per-tile power-of-two seed
                                   scaling, TMA-fed weight gradient without a conversion pass; PE_RES_F5 (K = 5) and PE_RES_F7 (K = 4), hidden

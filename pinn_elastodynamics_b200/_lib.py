@@ -23,12 +23,13 @@ PE_TILE_POINTS = 32
 PE_TC_TILE = 128
 
 RES_F5, RES_F7, RES_COLS, RES_TRACTION, RES_DT = 0, 1, 2, 3, 4
-ENGINE_SIMT_FP32, ENGINE_TCS_TF32X3, ENGINE_TCS_TF32, ENGINE_TCF = 0, 5, 6, 8
+ENGINE_SIMT_FP32, ENGINE_TCS_TF32X3, ENGINE_TCS_TF32, ENGINE_TCF, ENGINE_TCF_F16FWD = 0, 5, 6, 8, 9
 # 'tcf'  : fp16-pair tcgen05 engine (csrc/pe_tcf.cu): fp32-grade (measured <= 7e-7 on loss terms, <= 5e-6 on gradient blocks, <= 8.3e-6 on the
 #          reference's 20-step Adam curves: profiles/r2_refgold_report_tcf.jsonl) -- what 'auto' selects
 # 'tc3s' : TF32x3 tcgen05 engine (csrc/pe_tcs.cu), measured 5e-6 .. 8e-6 / 3.3e-5: A/B partner only;  'tc1s': its single-pass TF32 mode
 # 'simt' : fp32 FFMA engine, any width, every residual kind: the parity anchor
-ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3s': ENGINE_TCS_TF32X3, 'tc1s': ENGINE_TCS_TF32, 'tcf': ENGINE_TCF,
+# 'tcf16': 'tcf' with single-product fp16 forward GEMMs (BASELINE config 3's 16-bit forward / fp32 gradient mode; ~1e-3 class)
+ENGINES = {'simt': ENGINE_SIMT_FP32, 'tc3s': ENGINE_TCS_TF32X3, 'tc1s': ENGINE_TCS_TF32, 'tcf': ENGINE_TCF, 'tcf16': ENGINE_TCF_F16FWD,
            'auto': ENGINE_TCF}             # terms / networks the tensor-core engine does not implement run on the SIMT engine (engine.py build())
 
 

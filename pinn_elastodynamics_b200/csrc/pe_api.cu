@@ -17,7 +17,7 @@ void pe_set_error(const char* fmt, ...) {
 
 int pe_launch_resid_tcs(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
-int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
+int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2);
 
 // ---- sizing shared by the tcgen05 engines: 128-point tiles, one persistent CTA per SM (= one gradient-partial slot each); per slot a stash
@@ -122,7 +122,7 @@ extern "C" int pe_plan_bias_offset(const pe_plan* plan, int l) { return (plan &&
 extern "C" int pe_plan_weight_ld(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.ldw[l] : -1; }
 
 static bool is_tcs(int engine) { return engine == PE_ENGINE_TCS_TF32X3 || engine == PE_ENGINE_TCS_TF32; }
-static bool is_tcf(int engine) { return engine == PE_ENGINE_TCF; }
+static bool is_tcf(int engine) { return engine == PE_ENGINE_TCF || engine == PE_ENGINE_TCF_F16FWD; }
 static bool is_tc(int engine) { return is_tcs(engine) || is_tcf(engine); }
 
 extern "C" int pe_engine_supported(const pe_plan* plan, int kind, int K, int engine) {
@@ -245,7 +245,7 @@ static int residual_common(const pe_plan* plan, const pe_term_desc* term, int K,
             n_eff = PE_TC_TILE * ((n_local + PE_TC_TILE - 1) / PE_TC_TILE + (n2_local + PE_TC_TILE - 1) / PE_TC_TILE);
         }
         if (is_tcf(engine))
-            return pe_launch_resid_tcf(plan, a, K, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
+            return pe_launch_resid_tcf(plan, a, K, engine == PE_ENGINE_TCF_F16FWD ? 1 : 0, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
         return pe_launch_resid_tcs(plan, a, K, engine == PE_ENGINE_TCS_TF32 ? 1 : 0, pe_plan_slots(plan, n_eff, K, engine), (cudaStream_t)stream, term2, d_points2, n2_local, d_aux2);
     }
     pe_set_error("unknown engine %d", engine);

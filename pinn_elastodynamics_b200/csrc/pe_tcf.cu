@@ -54,7 +54,7 @@ constexpr int F_IMG_LAYER = 2 * F_IMG;            // forward image, adjoint imag
 constexpr int F_ONES = 0;                                     // 1,024 B of fp16 ones: B operand of the bias-gradient MMAs
 constexpr int F_ACT = 1024;                                   // NS x (hi plane | lo plane)
 constexpr int F_R = F_ACT + TC_MAX_STREAMS * F_STREAM;        // 144,384: forward: two weight images; reverse: adjoint image + two staging buffers
-constexpr int F_STG = F_R + F_IMG;                            // four staging slots of one plane each at F_STG + s * F_PLANE
+constexpr int F_STG = F_R + F_IMG;                            // two staging slots of one stream (hi plane | lo plane) each at F_STG + s * F_STREAM
 constexpr int F_MISC = F_R + F_IMG + 2 * F_STREAM;            // 218,112: mbarriers + TMEM base slot + tile scale
 constexpr int F_COORD = F_MISC + 256;
 constexpr int F_RED = F_COORD + 128 * 16;
@@ -64,7 +64,7 @@ constexpr int F_TOTAL = F_W0 + 1024;                          // 229,632
 static_assert(2 * F_IMG <= F_IMG + 2 * F_STREAM, "the forward image double buffer lives inside the reverse-sweep region");
 static_assert(F_TOTAL <= 227 * 1024, "shared memory map exceeds the 227 KB opt-in limit");
 constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SEMPTY = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144;   // byte offsets in F_MISC
-constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW: 56 hi-hi + 56 cross; bias: 8 + 8)
+constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW tile: 128 lanes x 112; bias tile: 128 lanes x 8)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 template <int NS> __device__ __forceinline__ int grp_first(int g) { return g == 0 ? 0 : (g == 1 ? 1 : 3); }
@@ -72,21 +72,77 @@ template <int NS> __device__ __forceinline__ int grp_count(int g) { return g == 
 
 // kind::f16 instruction descriptors, fp16 x fp16, fp32 accumulate
 __device__ __forceinline__ uint32_t idesc_km(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }                        // K-major, M = 128
-__device__ __forceinline__ uint32_t idesc_mn(int N) { return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (4u << 24); }  // MN-major, M = 64
+__device__ __forceinline__ uint32_t idesc_mn(int N) { return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }  // MN-major, M = 128
 
-// 4 floats -> fp16 pair planes (hi, lo scaled by 2^11), each packed into a uint2
-__device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
-    const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn((x[0] - f01.x) * LO_SCALE, (x[1] - f01.y) * LO_SCALE);
-    const __half2 l23 = __floats2half2_rn((x[2] - f23.x) * LO_SCALE, (x[3] - f23.y) * LO_SCALE);
-    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+// ---- epilogue arithmetic on PAIRS of units: sm_100 executes add / mul / fma on two packed fp32 values per instruction (FADD2 / FMUL2 /
+// FFMA2), which halves the instruction count of everything that is element-wise in the unit index: the operand split and join, the
+// polynomial branch of tanh, the chain rule and its adjoint.
+typedef float2 f2;
+__device__ __forceinline__ f2 F2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 F2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+// two values -> fp16 pair (hi = fp16(x), lo = fp16((x - hi) 2^11); x - hi is exact in fp32)
+__device__ __forceinline__ void split2(f2 x, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x.x, x.y);
+    const f2 d = __fmul2_rn(__ffma2_rn(__half22float2(h), F2(-1.f), x), F2(LO_SCALE));
+    hi = h2_bits(h);
+    lo = h2_bits(__floats2half2_rn(d.x, d.y));
 }
-__device__ __forceinline__ void join4(const uint2& hi, const uint2& lo, float (&x)[4]) {
-    const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
-    const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
-    x[0] = fmaf(l01.x, LO_INV, h01.x); x[1] = fmaf(l01.y, LO_INV, h01.y); x[2] = fmaf(l23.x, LO_INV, h23.x); x[3] = fmaf(l23.y, LO_INV, h23.y);
+__device__ __forceinline__ f2 join2(uint32_t hi, uint32_t lo) {
+    return __ffma2_rn(__half22float2(bits_h2(lo)), F2(LO_INV), __half22float2(bits_h2(hi)));
+}
+__device__ __forceinline__ void split4(f2 x01, f2 x23, uint2& hi, uint2& lo) { split2(x01, hi.x, lo.x); split2(x23, hi.y, lo.y); }
+
+// tanh of two values: pe_dev::tanh_branchfree with the odd polynomial evaluated on the packed pair (same coefficients, same 0.3 switch)
+__device__ __forceinline__ f2 tanh2(f2 x) {
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fabsf(x.x) * 2.885390081777927f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fabsf(x.y) * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(e0 + 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(e1 + 1.0f));
+    const float b0 = copysignf(fmaf(-2.0f, r0, 1.0f), x.x), b1 = copysignf(fmaf(-2.0f, r1, 1.0f), x.y);
+    const f2 x2 = __fmul2_rn(x, x);
+    f2 p = F2(-1382.0f / 155925.0f);
+    p = __ffma2_rn(p, x2, F2(62.0f / 2835.0f));
+    p = __ffma2_rn(p, x2, F2(-17.0f / 315.0f));
+    p = __ffma2_rn(p, x2, F2(2.0f / 15.0f));
+    p = __ffma2_rn(p, x2, F2(-1.0f / 3.0f));
+    const f2 sm = __ffma2_rn(__fmul2_rn(x, x2), p, x);
+    return F2(fabsf(x.x) < 0.3f ? sm.x : b0, fabsf(x.y) < 0.3f ? sm.y : b1);
+}
+
+// adjoint of the tanh layer (pe_dev::act_bwd) for two units at once.  A = stashed outputs (a, a_x, ..), ab = adjoints of the
+// outputs; returns the adjoints of the pre-activations in ab.  1 / s through the approximate reciprocal (1 ulp), guarded for s = 0.
+template <int K>
+__device__ __forceinline__ void act_bwd2(f2 (&ab)[K], const f2 (&A)[K]) {
+    const f2 a = A[0];
+    const f2 s = F2(fmaf(-a.x, a.x, 1.f), fmaf(-a.y, a.y, 1.f));
+    f2 acc = __fmul2_rn(A[1], ab[1]);
+    acc = __ffma2_rn(A[2], ab[2], acc);
+    acc = __ffma2_rn(A[3], ab[3], acc);                                             // s z_k = A_k
+    f2 zv = __ffma2_rn(__fmul2_rn(a, acc), F2(-2.f), __fmul2_rn(s, ab[0]));
+    if (K == 5) {
+        float i0, i1;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(s.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(s.y));
+        const f2 inv_s = F2(s.x > 0.f ? i0 : 0.f, s.y > 0.f ? i1 : 0.f);
+        const f2 zt = __fmul2_rn(A[3], inv_s);                                      // z_t
+        const f2 aA3 = __fmul2_rn(a, A[3]);
+        const f2 sztt = __ffma2_rn(__fmul2_rn(aA3, F2(2.f)), zt, A[K - 1]);         // s z_tt = a_tt + 2 a s z_t^2
+        zv = __ffma2_rn(__fmul2_rn(__fmul2_rn(a, sztt), F2(-2.f)), ab[K - 1], zv);
+        const f2 c = F2(fmaf(-3.f * a.x, a.x, 1.f), fmaf(-3.f * a.y, a.y, 1.f));
+        zv = __ffma2_rn(__fmul2_rn(__fmul2_rn(__fmul2_rn(c, A[3]), zt), F2(-2.f)), ab[K - 1], zv);
+        const f2 zb3 = __ffma2_rn(s, ab[3], __fmul2_rn(__fmul2_rn(aA3, F2(-4.f)), ab[K - 1]));
+        ab[K - 1] = __fmul2_rn(s, ab[K - 1]);
+        ab[3] = zb3;
+        ab[1] = __fmul2_rn(s, ab[1]); ab[2] = __fmul2_rn(s, ab[2]);
+    } else {
+#pragma unroll
+        for (int k = 1; k < K; ++k) ab[k] = __fmul2_rn(s, ab[k]);
+    }
+    ab[0] = zv;
 }
 
 // Operand images per matrix m: forward B operand [n = out unit j][k = in unit i] at [(i >> 3)][j][i & 7] and adjoint B operand
@@ -118,38 +174,51 @@ struct TcfArgs {
     const float* aux2;
     int n2;
     float inv_n2;
+    int fast;                   // 1 = 16-bit forward mode: forward layer GEMMs as single fp16 products (adjoint / weight-gradient GEMMs stay fp16 pairs)
     unsigned long long* prof;   // PROF instantiation: 32 cycle counters (0..15 epilogue thread 0, 16..31 issuer) of CTA 0
 };
 
 #define TCF_PROF(slot) do { if (PROF) { if (prof_on) { const long long now_ = clock64(); atomicAdd(args.prof + (slot), (unsigned long long)(now_ - prof_t)); prof_t = now_; } } } while (0)
 
-// MMAs of one layer GEMM for streams [k0, k0 + nk): per K-step of 16 the two cross products, then the hi x hi products (the first of them
+// ---- lean MMA issue.  One thread issues every tcgen05.mma of the kernel, and that thread executes ordinary (non-uniform) code: each MMA costs
+// it the moves of its operands into uniform registers plus whatever integer work builds the descriptors.  Measured (tests/probe_umma_timing.py):
+// with descriptors rebuilt by shifts / masks per MMA the ISSUE takes ~77 cycles per instruction for every shape up to N = 128 -- more than the
+// tensor pipe needs to execute them -- so all loops over streams and K-steps are fully unrolled here and a descriptor is one 32-bit add of a
+// compile-time constant to a base word: the matrix start address (bits 0..13, 16-byte units; all offsets stay below 2^14) with the leading-
+// dimension offset in bits 16..29; the upper word (stride offset, version bit) is shared by all descriptors of a family.
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+
+// MMAs of one layer GEMM for streams [K0, K0 + NK): per K-step of 16 the two cross products, then the hi x hi products (the first of them
 // scales the accumulated cross products by 2^-11); K-steps interleaved across the streams of the call, so that consecutive MMAs do not
-// accumulate into the same tile when the group has more than one stream.
-__device__ __forceinline__ void issue_streams(int k0, int nk, uint32_t tbase, uint32_t act_s, uint32_t img_s, int N, int kdim) {
-    const int ksteps = (kdim + 15) >> 4;
-    const uint32_t id = idesc_km(N);
-#pragma unroll 1
-    for (int s = 0; s < ksteps; ++s) {
-        const uint64_t bhi = sdesc(img_s + 2 * s * 1024, 1024, 128), blo = sdesc(img_s + F_IMG_HALF + 2 * s * 1024, 1024, 128);
+// accumulate into the same tile when the group has more than one stream.  a_lo / b_lo: base words of the activation planes (stream 0, hi
+// plane, K-step 0) and of the weight image (hi half); km_hi: upper word of K-major descriptors (SBO = 128).
+// fast: 16-bit forward mode (BASELINE config 3, "16-bit forward / fp32 gradient"): only the hi x hi products, 4 MMAs per stream and layer.
+template <int K0, int NK>
+__device__ __forceinline__ void issue_group(uint32_t tbase, uint32_t a_lo, uint32_t b_lo, uint32_t km_hi, uint32_t id, int ksteps, bool fast = false) {
 #pragma unroll
-        for (int k = 0; k < TC_MAX_STREAMS; ++k)
-            if (k < nk) mma_bf16_ss(tbase + T_ACC + 64u * (k0 + k), sdesc(act_s + (uint32_t)((k0 + k) * F_STREAM + 2 * s * F_CH), F_CH, 128), blo, id, s > 0);
+    for (int s = 0; s < 4; ++s)
+        if (s < ksteps && !fast) {
+            const uint64_t bhi = mk_desc(b_lo + (uint32_t)((2 * s * 1024) >> 4), km_hi), blo = mk_desc(b_lo + (uint32_t)((F_IMG_HALF + 2 * s * 1024) >> 4), km_hi);
 #pragma unroll
-        for (int k = 0; k < TC_MAX_STREAMS; ++k)
-            if (k < nk) mma_bf16_ss(tbase + T_ACC + 64u * (k0 + k), sdesc(act_s + (uint32_t)((k0 + k) * F_STREAM + F_PLANE + 2 * s * F_CH), F_CH, 128), bhi, id, 1u);
-    }
-#pragma unroll 1
-    for (int s = 0; s < ksteps; ++s) {
-        const uint64_t bhi = sdesc(img_s + 2 * s * 1024, 1024, 128);
+            for (int k = K0; k < K0 + NK; ++k)
+                mma_bf16_ss(tbase + T_ACC + 64u * k, mk_desc(a_lo + (uint32_t)((k * F_STREAM + 2 * s * F_CH) >> 4), km_hi), blo, id, s > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < TC_MAX_STREAMS; ++k)
-            if (k < nk) {
-                const uint64_t a = sdesc(act_s + (uint32_t)((k0 + k) * F_STREAM + 2 * s * F_CH), F_CH, 128);
-                if (s == 0) mma_f16_ss_scaled11(tbase + T_ACC + 64u * (k0 + k), a, bhi, id);
-                else mma_bf16_ss(tbase + T_ACC + 64u * (k0 + k), a, bhi, id, 1u);
+            for (int k = K0; k < K0 + NK; ++k)
+                mma_bf16_ss(tbase + T_ACC + 64u * k, mk_desc(a_lo + (uint32_t)((k * F_STREAM + F_PLANE + 2 * s * F_CH) >> 4), km_hi), bhi, id, 1u);
+        }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (s < ksteps) {
+            const uint64_t bhi = mk_desc(b_lo + (uint32_t)((2 * s * 1024) >> 4), km_hi);
+#pragma unroll
+            for (int k = K0; k < K0 + NK; ++k) {
+                const uint64_t a = mk_desc(a_lo + (uint32_t)((k * F_STREAM + 2 * s * F_CH) >> 4), km_hi);
+                if (s == 0 && !fast) mma_f16_ss_scaled11(tbase + T_ACC + 64u * k, a, bhi, id);
+                else mma_bf16_ss(tbase + T_ACC + 64u * k, a, bhi, id, s > 0 ? 1u : 0u);
             }
-    }
+        }
 }
 
 template <int NS, bool PROF>
@@ -199,7 +268,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     if (tid == 0) {
         for (int g = 0; g < 3; ++g) { mbar_init(bar_acc + 8 * g, 1); mbar_init(bar_act + 8 * g, F_EPI); }
         for (int b = 0; b < 2; ++b) mbar_init(bar_img + 8 * b, 1);
-        for (int b = 0; b < 4; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, 1); }
         mbar_init(bar_dw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -224,6 +293,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         if (warp == F_CTRL && lane == 0) {
             uint32_t pact = 0, pimg = 0, psfull = 0, psempty = 0;     // parity bits of the phases this thread waits for next
             uint32_t n_acc2 = 0, n_dw = 0;
+            const bool fast = args.fast != 0;
             auto load_fwd = [&](int i) {
                 const uint32_t b = (uint32_t)(i & 1);
                 mbar_expect_tx(bar_img + 8 * b, F_IMG);
@@ -231,6 +301,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
             };
             auto wait_img = [&](uint32_t b) { mbar_wait(bar_img + 8 * b, (pimg >> b) & 1u); pimg ^= 1u << b; };
             auto wait_act = [&](int g) { mbar_wait(bar_act + 8 * g, (pact >> g) & 1u); pact ^= 1u << g; };
+            // descriptor base words (see issue_group): K-major activation planes / weight images, MN-major planes / staging slots / ones block
+            const uint32_t km_hi = desc_hi(128), mn_hi = desc_hi(F_CH);
+            const uint32_t a_lo = desc_lo(act_s, F_CH), b_lo0 = desc_lo(r_s, 1024), b_lo1 = desc_lo(r_s + F_IMG, 1024);
+            const uint32_t z_lo = desc_lo(act_s, 128), g_lo = desc_lo(stg_s, 128);
+            const uint64_t d_ones = mk_desc(desc_lo(ones_s, 128), desc_hi(256));
             load_fwd(2);
             if (L >= 3) load_fwd(3);
             if (PROF) prof_t = clock64();
@@ -246,7 +321,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         wait_act(g);
                         TCF_PROF(17 + 2 * g);
                         fence_after();
-                        issue_streams(grp_first<NS>(g), grp_count<NS>(g), tbase, act_s, r_s + b * F_IMG, NF, lay.d[l - 1]);
+                        {
+                            const uint32_t b_lo = b ? b_lo1 : b_lo0, id = idesc_km(NF);
+                            const int ksteps = (lay.d[l - 1] + 15) >> 4;
+                            if (g == 0) issue_group<0, 1>(tbase, a_lo, b_lo, km_hi, id, ksteps, fast);
+                            else if (g == 1) issue_group<1, 2>(tbase, a_lo, b_lo, km_hi, id, ksteps, fast);
+                            else issue_group<3, NS - 3>(tbase, a_lo, b_lo, km_hi, id, ksteps, fast);
+                        }
                         mma_commit(bar_acc + 8 * g);
                         TCF_PROF(18 + 2 * g);
                         if (g == 2) ++n_acc2;
@@ -267,16 +348,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 for (int l = L; l >= 2; --l) {
                     const int dout = lay.d[l];
                     const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;     // outputs of layer l-1 = inputs A of layer l
-                    // the stashed planes of A_{l-1} come back one plane (hi or lo of one stream) per bulk copy into four staging slots:
-                    // item i = 2 k + (0: hi plane, 1: lo plane) of stream k lives in slot i & 3
-                    constexpr int NI = 2 * NS;
-                    auto load_item = [&](int i) {
-                        const uint32_t sl = (uint32_t)(i & 3);
-                        mbar_expect_tx(bar_sfull + 8 * sl, F_PLANE);
-                        tma_load_1d(stg_s + sl * F_PLANE, stash_in + (size_t)i * F_PLANE, F_PLANE, bar_sfull + 8 * sl);
+                    // the stashed planes of A_{l-1} come back one stream (hi plane | lo plane, 28,672 B) per bulk copy into two staging slots
+                    auto load_stage = [&](int k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_expect_tx(bar_sfull + 8 * sb, F_STREAM);
+                        tma_load_1d(stg_s + sb * F_STREAM, stash_in + (size_t)k * F_STREAM, F_STREAM, bar_sfull + 8 * sb);
                     };
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) load_item(i);   // all four slots are free: the previous layer's DW phase is complete
+                    load_stage(0);                              // both slots are free: the previous layer's DW phase is complete
+                    load_stage(1);
                     if (l > 2) {                                // pull the planes of the next (shallower) layer towards L2 while this layer runs
                         const uint8_t* nxt = stash + (size_t)(l - 3) * STASH_LAYER;
 #pragma unroll
@@ -288,63 +367,49 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     wait_act(0); wait_act(1); wait_act(2);
                     TCF_PROF(25);
                     fence_after();
-                    issue_streams(0, NS, tbase, act_s, r_s, 64, dout);
+                    issue_group<0, NS>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
                     mma_commit(bar_acc);
                     mma_commit(bar_acc + 8);
                     mma_commit(bar_acc + 16);
                     ++n_acc2;
                     TCF_PROF(26);
-                    // ---- weight gradient  dW = sum_k A_k^T Zbar_k  (K = 128 points, 8 K-steps of 16): columns 0..55 of the tile take Ah^T Zh,
-                    //      columns 56..111 the cross products Ah^T Zl + Al^T Zh (factor 2^11, resolved when the tile is drained)
+                    // ---- weight gradient  dW = sum_k A_k^T Zbar_k  (K = 128 points, 8 K-steps of 16) as ONE M = 128 MMA per K-step: the A operand is
+                    //      the staged stream read MN-major, rows 0..55 = Ah units, rows 56..111 = Al units (rows 112..127: whatever follows the slot,
+                    //      ignored); the B operand [Zh | Zl] (N = 112).  Tile: rows i, columns j: Ah^T Zh | rows i, columns 56 + j: Ah^T Zl | rows 56 + i,
+                    //      columns j: Al^T Zh (the cross products carry 2^11 and are resolved when the tile is drained).  The MMA count, not the MMA
+                    //      size, is what the tensor pipe charges for at these shapes (tests/probe_umma_timing.py: ~64 cycles per instruction up to N = 128).
                     const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
-                    const uint32_t id112 = idesc_mn(112), id56 = idesc_mn(56), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
+                    const uint32_t id112 = idesc_mn(112), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
 #pragma unroll 1
-                    for (int i = 0; i < NI; ++i) {
-                        const uint32_t sl = (uint32_t)(i & 3);
-                        const int k = i >> 1;
-                        mbar_wait(bar_sfull + 8 * sl, (psfull >> sl) & 1u);
-                        psfull ^= 1u << sl;
-                        const uint32_t a_s = stg_s + sl * F_PLANE;
-                        const uint32_t z_hi = act_s + (uint32_t)(k * F_STREAM), z_lo = z_hi + F_PLANE;
-                        if (!(i & 1)) {                                      // hi plane:  Ah^T [Zh | Zl]
-#pragma unroll 1
-                            for (int s = 0; s < 8; ++s) {
-                                const uint32_t o = (uint32_t)(s * 256);      // 16 points x 16 B
-                                const uint64_t da = sdesc(a_s + o, 128, F_CH);
-                                const uint32_t first = (i > 0 || s > 0) ? 1u : 0u;
-                                if (nzc == 7) {                              // the two Z planes are contiguous: one N = 112 MMA
-                                    mma_bf16_ss(tbase + T_DW, da, sdesc(z_hi + o, 128, F_CH), id112, first);
-                                } else {
-                                    mma_bf16_ss(tbase + T_DW, da, sdesc(z_hi + o, 128, F_CH), idz, first);
-                                    mma_bf16_ss(tbase + T_DW + 56, da, sdesc(z_lo + o, 128, F_CH), idz, first);
-                                }
-                            }
-                        } else {                                             // lo plane:  Al^T Zh
-#pragma unroll 1
-                            for (int s = 0; s < 8; ++s) {
-                                const uint32_t o = (uint32_t)(s * 256);
-                                mma_bf16_ss(tbase + T_DW + 56, sdesc(a_s + o, 128, F_CH), sdesc(z_hi + o, 128, F_CH), nzc == 7 ? id56 : idz, 1u);
+                    for (int k = 0; k < NS; ++k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
+                        psfull ^= 1u << sb;
+                        const uint32_t ga = g_lo + sb * (uint32_t)(F_STREAM >> 4);
+                        const uint32_t zh = z_lo + (uint32_t)k * (uint32_t)(F_STREAM >> 4), zl = zh + (uint32_t)(F_PLANE >> 4);
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {                        // K-steps of 16 points = 256 B
+                            const uint64_t da = mk_desc(ga + 16u * s, mn_hi);
+                            const uint32_t first = (k > 0 || s > 0) ? 1u : 0u;
+                            if (nzc == 7) {                                  // the two Z planes are contiguous: one N = 112 MMA
+                                mma_bf16_ss(tbase + T_DW, da, mk_desc(zh + 16u * s, mn_hi), id112, first);
+                            } else {
+                                mma_bf16_ss(tbase + T_DW, da, mk_desc(zh + 16u * s, mn_hi), idz, first);
+                                mma_bf16_ss(tbase + T_DW + 56, da, mk_desc(zl + 16u * s, mn_hi), idz, first);
                             }
                         }
-                        if (i + 4 < NI) mma_commit(bar_sempty + 8 * sl);       // this slot is refilled (item i + 4) once its MMAs are complete
-                        if (i >= 1 && i + 3 < NI) {                          // ... which is waited for one item later, behind the next item's MMAs
-                            const uint32_t ob = (uint32_t)((i - 1) & 3);
+                        if (k + 2 < NS) mma_commit(bar_sempty + 8 * sb);       // this slot is refilled (stream k + 2) once its MMAs are complete
+                        if (k >= 1 && k + 1 < NS) {                          // ... which is waited for one stream later, behind the next stream's MMAs
+                            const uint32_t ob = sb ^ 1u;
                             mbar_wait(bar_sempty + 8 * ob, (psempty >> ob) & 1u);
                             psempty ^= 1u << ob;
-                            load_item(i + 3);
+                            load_stage(k + 1);
                         }
                     }
-                    {   // bias gradient: column 0 of  Zh^T 1  (and of  Zl^T 1): the value-stream plane is the MN-major A operand (M = 64 units;
-                        // its eighth chunk is the first chunk of the lo plane: rows 56..63, ignored), a block of ones the B operand
-                        const uint32_t z_hi = act_s, z_lo = act_s + F_PLANE;
-                        const uint64_t d1 = sdesc(ones_s, 128, 256);
-#pragma unroll 1
-                        for (int s = 0; s < 8; ++s) {
-                            const uint32_t o = (uint32_t)(s * 256);
-                            mma_bf16_ss(tbase + T_BIAS, sdesc(z_hi + o, 128, F_CH), d1, id8, s > 0 ? 1u : 0u);
-                            mma_bf16_ss(tbase + T_BIAS + 8, sdesc(z_lo + o, 128, F_CH), d1, id8, s > 0 ? 1u : 0u);
-                        }
-                    }
+                    // bias gradient: column 0 of  [Zh | Zl]^T 1: the value-stream planes as MN-major A operand (M = 128: rows 0..55 sums of Zh, rows
+                    // 56..111 sums of Zl), a block of ones as B operand (N = 8)
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_BIAS, mk_desc(z_lo + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
                     mma_commit(bar_dw);
                     ++n_dw;
                     TCF_PROF(27);
@@ -374,18 +439,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         uint32_t pacc = 0, pdw = 0;
         auto wait_acc = [&](int g) { mbar_wait(bar_acc + 8 * g, (pacc >> g) & 1u); pacc ^= 1u << g; };
         auto publish = [&](int g) { mbar_arrive(bar_act + 8 * g); };
-        // planes in shared memory and in the stash (global) were written through the generic proxy; their next readers are MMAs and bulk
-        // copies (async proxy)
-        auto publish_fences = [&]() { asm volatile("fence.proxy.async;" ::: "memory"); fence_before(); };
+        // planes in shared memory were written through the generic proxy and are read next by MMAs (async proxy): a shared-memory proxy fence
+        // per publish.  The stashed copies in global memory are read by bulk copies only in the reverse sweep: ONE all-state-space proxy fence
+        // at the end of the forward sweep (publish_fences_global) covers them -- a global fence per publish makes every epilogue phase wait for
+        // its stash stores to be acknowledged by L2 (measured: the forward epilogue phases were bound by it, not by their instructions).
+        auto publish_fences = [&]() { fence_async_smem(); fence_before(); };
+        auto publish_fences_global = [&]() { asm volatile("fence.proxy.async;" ::: "memory"); fence_before(); };
         auto c4_lo = [&](int d) { return ((d + 3) >> 2) * h / F_NH; };
         auto c4_hi = [&](int d) { return ((d + 3) >> 2) * (h + 1) / F_NH; };
         float tsum[PE_MAX_TERMS], tsum2[PE_MAX_TERMS];
 #pragma unroll
         for (int i = 0; i < PE_MAX_TERMS; ++i) { tsum[i] = 0.f; tsum2[i] = 0.f; }
         // 4 units (group c4) of stream k of this thread's point -> hi / lo planes in shared memory [and in the stash layer `st`]
-        auto put4 = [&](uint8_t* st, int k, int c4, const float (&v)[4]) {
+        auto put4 = [&](uint8_t* st, int k, int c4, f2 v01, f2 v23) {
             uint2 hi, lo;
-            split4(v, hi, lo);
+            split4(v01, v23, hi, lo);
             const int o = k * F_STREAM + (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
             *reinterpret_cast<uint2*>(act + o) = hi;
             *reinterpret_cast<uint2*>(act + o + F_PLANE) = lo;
@@ -394,9 +462,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 __stcg(reinterpret_cast<uint2*>(st + o + F_PLANE), lo);
             }
         };
-        auto get4 = [&](int k, int c4, float (&v)[4]) {          // this thread's own entries of the planes in shared memory
+        auto get4 = [&](int k, int c4, f2& v01, f2& v23) {       // this thread's own entries of the planes in shared memory
             const int o = k * F_STREAM + (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
-            join4(*reinterpret_cast<const uint2*>(act + o), *reinterpret_cast<const uint2*>(act + o + F_PLANE), v);
+            const uint2 hi = *reinterpret_cast<const uint2*>(act + o), lo = *reinterpret_cast<const uint2*>(act + o + F_PLANE);
+            v01 = join2(hi.x, lo.x); v23 = join2(hi.y, lo.y);
         };
 
         if (PROF) prof_t = clock64();
@@ -447,7 +516,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         for (int k = 0; k < NS; ++k) o[k][u] = z[k];
                     }
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) put4(stash, k, c4, o[k]);                 // stash layer 0 = outputs of layer 1
+                    for (int k = 0; k < NS; ++k) put4(stash, k, c4, F2(o[k][0], o[k][1]), F2(o[k][2], o[k][3]));      // stash layer 0 = outputs of layer 1
                 }
                 publish_fences();
                 publish(0); publish(1); publish(2);
@@ -468,9 +537,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     tm_ld4(tlane + T_ACC + 4 * c4, z);
                     const float4 b4 = *reinterpret_cast<const float4*>(bl + 4 * c4);
                     tm_wait_ld();
-                    z[0] = tanh_branchfree(z[0] + b4.x); z[1] = tanh_branchfree(z[1] + b4.y);
-                    z[2] = tanh_branchfree(z[2] + b4.z); z[3] = tanh_branchfree(z[3] + b4.w);
-                    put4(st, 0, c4, z);
+                    put4(st, 0, c4, tanh2(__fadd2_rn(F2(z[0], z[1]), F2(b4.x, b4.y))), tanh2(__fadd2_rn(F2(z[2], z[3]), F2(b4.z, b4.w))));
                 }
                 publish_fences();
                 publish(0);
@@ -481,19 +548,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 fence_after();
 #pragma unroll 1
                 for (int c4 = lo4; c4 < hi4; ++c4) {
-                    float av[4], z1[4], z2[4];
+                    float z1[4], z2[4];
+                    f2 a01, a23;
                     tm_ld4(tlane + T_ACC + 64 + 4 * c4, z1);
                     tm_ld4(tlane + T_ACC + 128 + 4 * c4, z2);
-                    get4(0, c4, av);
+                    get4(0, c4, a01, a23);
+                    const f2 s01 = F2(fmaf(-a01.x, a01.x, 1.f), fmaf(-a01.y, a01.y, 1.f)), s23 = F2(fmaf(-a23.x, a23.x, 1.f), fmaf(-a23.y, a23.y, 1.f));
                     tm_wait_ld();
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float s = fmaf(-av[u], av[u], 1.f);
-                        z1[u] *= s;
-                        z2[u] *= s;
-                    }
-                    put4(st, 1, c4, z1);
-                    put4(st, 2, c4, z2);
+                    put4(st, 1, c4, __fmul2_rn(s01, F2(z1[0], z1[1])), __fmul2_rn(s23, F2(z1[2], z1[3])));
+                    put4(st, 2, c4, __fmul2_rn(s01, F2(z2[0], z2[1])), __fmul2_rn(s23, F2(z2[2], z2[3])));
                 }
                 publish_fences();
                 publish(1);
@@ -504,22 +567,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 fence_after();
 #pragma unroll 1
                 for (int c4 = lo4; c4 < hi4; ++c4) {
-                    float av[4], z3[4], z4[4];
+                    float z3[4], z4[4];
+                    f2 a01, a23;
                     tm_ld4(tlane + T_ACC + 192 + 4 * c4, z3);
                     if (NS == 5) tm_ld4(tlane + T_ACC + 256 + 4 * c4, z4);
-                    get4(0, c4, av);
+                    get4(0, c4, a01, a23);
+                    const f2 s01 = F2(fmaf(-a01.x, a01.x, 1.f), fmaf(-a01.y, a01.y, 1.f)), s23 = F2(fmaf(-a23.x, a23.x, 1.f), fmaf(-a23.y, a23.y, 1.f));
                     tm_wait_ld();
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float a = av[u];
-                        const float s = fmaf(-a, a, 1.f);
-                        const float zt = z3[u];
-                        const float at = s * zt;
-                        z3[u] = at;
-                        if (NS == 5) z4[u] = fmaf(s, z4[u], -2.f * a * at * zt);
+                    const f2 zt01 = F2(z3[0], z3[1]), zt23 = F2(z3[2], z3[3]);
+                    const f2 at01 = __fmul2_rn(s01, zt01), at23 = __fmul2_rn(s23, zt23);
+                    put4(st, 3, c4, at01, at23);
+                    if (NS == 5) {       // a_tt = s z_tt - 2 a a_t z_t
+                        const f2 q01 = __fmul2_rn(__fmul2_rn(a01, at01), zt01), q23 = __fmul2_rn(__fmul2_rn(a23, at23), zt23);
+                        put4(st, 4, c4, __ffma2_rn(q01, F2(-2.f), __fmul2_rn(s01, F2(z4[0], z4[1]))), __ffma2_rn(q23, F2(-2.f), __fmul2_rn(s23, F2(z4[2], z4[3]))));
                     }
-                    put4(st, 3, c4, z3);
-                    if (NS == 5) put4(st, 4, c4, z4);
                 }
                 publish_fences();
                 publish(2);
@@ -581,13 +642,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     // seeds Zbar_L: units 0..7 in groups 0 and 1 (the only chunk the adjoint / weight-gradient MMAs of the output layer use)
 #pragma unroll
                     for (int k = 0; k < NS; ++k) {
-                        const float v0[4] = {Y[k][0] * sigma, Y[k][1] * sigma, Y[k][2] * sigma, Y[k][3] * sigma};
-                        const float v1[4] = {Y[k][4] * sigma, Y[k][5] * sigma, Y[k][6] * sigma, Y[k][7] * sigma};
-                        put4(nullptr, k, 0, v0);
-                        put4(nullptr, k, 1, v1);
+                        put4(nullptr, k, 0, F2(Y[k][0] * sigma, Y[k][1] * sigma), F2(Y[k][2] * sigma, Y[k][3] * sigma));
+                        put4(nullptr, k, 1, F2(Y[k][4] * sigma, Y[k][5] * sigma), F2(Y[k][6] * sigma, Y[k][7] * sigma));
                     }
                 }
-                publish_fences();
+                publish_fences_global();                     // the whole stash of this tile before the reverse sweep's bulk copies
                 publish(0); publish(1); publish(2);
                 TCF_PROF(8);
             }
@@ -614,60 +673,81 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 pdw ^= 1u;
                 TCF_PROF(10);
                 fence_after();
-                {   // drain: weight-gradient rows i = 16*quadrant + lane (lane < 16); the unit groups share the columns; bias gradient = column 0
-                    const int quad = warp & 3;
-                    const int i = 16 * quad + lane;
+                {   // drain.  Tile rows r = 32 * quadrant + lane.  Rows r < din carry Ah^T Zh (columns j) and Ah^T Zl (columns 56 + j) of input unit
+                    // i = r; rows 56 <= r < 56 + din carry Al^T Zh of unit i = r - 56.  Two passes with a barrier in between, so that the two adds
+                    // every gradient element receives per tile always arrive in the same order (bitwise reproducible sums).  The unit groups of a
+                    // quadrant share the columns.  Bias gradient: column 0 of its tile, rows j (hi sums) and 56 + j (lo sums).
+                    // (tcgen05.ld is warp-collective: the loads sit behind warp-uniform conditions only, the lane's row decides about the adds)
+                    const int r0 = 32 * (warp & 3), r = r0 + lane;
                     const int ldw = lay.ldw[m];
                     float* gW = gpart + lay.woff[m];
                     float* gB = gpart + lay.boff[m];
                     const int nc8 = (dout + 7) >> 3;
-                    for (int c8 = h; c8 < nc8; c8 += F_NH) {
-                        const int c = 8 * c8;
-                        float v[8], vx[8];
-                        tm_ld8(tlane + T_DW + c, v);
-                        tm_ld8(tlane + T_DW + 56 + c, vx);
-                        tm_wait_ld();
-                        if (lane < 16 && i < din) {
+                    const float sc_lo = LO_INV * inv_sigma;
+                    if (r0 < din) {
+                        for (int c8 = h; c8 < nc8; c8 += F_NH) {
+                            const int c = 8 * c8;
+                            float v[8], vx[8];
+                            tm_ld8(tlane + T_DW + c, v);
+                            tm_ld8(tlane + T_DW + 56 + c, vx);
+                            tm_wait_ld();
+                            if (r < din) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) v[q] = fmaf(vx[q], LO_INV, v[q]) * inv_sigma;
-                            float* dst = gW + (size_t)i * ldw + c;
-                            if (c < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
-                            if (c + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+                                for (int q = 0; q < 8; ++q) v[q] = fmaf(vx[q], LO_INV, v[q]) * inv_sigma;
+                                float* dst = gW + (size_t)r * ldw + c;
+                                if (c < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+                                if (c + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+                            }
                         }
                     }
-                    if (h == F_NH - 1) {
-                        float vb[8], vbx[8];
+                    if (h == F_NH - 1 && r0 < dout) {
+                        float vb[8];
                         tm_ld8(tlane + T_BIAS, vb);
-                        tm_ld8(tlane + T_BIAS + 8, vbx);
                         tm_wait_ld();
-                        if (lane < 16 && i < dout) atomicAdd(gB + i, fmaf(vbx[0], LO_INV, vb[0]) * inv_sigma);
+                        if (r < dout) atomicAdd(gB + r, vb[0] * inv_sigma);
+                    }
+                    named_bar_sync(1, F_EPI);
+                    if (r0 + 32 > 56 && r0 < 56 + din) {
+                        for (int c8 = h; c8 < nc8; c8 += F_NH) {
+                            const int c = 8 * c8;
+                            float v[8];
+                            tm_ld8(tlane + T_DW + c, v);
+                            tm_wait_ld();
+                            if (r >= 56 && r < 56 + din) {
+                                float* dst = gW + (size_t)(r - 56) * ldw + c;
+                                if (c < ldw) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0] * sc_lo, v[1] * sc_lo, v[2] * sc_lo, v[3] * sc_lo));
+                                if (c + 4 < ldw) atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4] * sc_lo, v[5] * sc_lo, v[6] * sc_lo, v[7] * sc_lo));
+                            }
+                        }
+                    }
+                    if (h == F_NH - 1 && r0 + 32 > 56 && r0 < 56 + dout) {
+                        float vb[8];
+                        tm_ld8(tlane + T_BIAS, vb);
+                        tm_wait_ld();
+                        if (r >= 56 && r < 56 + dout) atomicAdd(gB + (r - 56), vb[0] * sc_lo);
                     }
                 }
                 TCF_PROF(11);
                 // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs (hi + lo)
 #pragma unroll 1
                 for (int c4 = lo4; c4 < hi4; ++c4) {
-                    float ab[NS][4], Av[NS][4];
+                    float ab[NS][4];
+                    f2 A01[NS], A23[NS], b01[NS], b23[NS];
 #pragma unroll
                     for (int k = 0; k < NS; ++k) tm_ld4(tlane + T_ACC + 64 * k + 4 * c4, ab[k]);
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) join4(nh[k], nl[k], Av[k]);
+                    for (int k = 0; k < NS; ++k) { A01[k] = join2(nh[k].x, nl[k].x); A23[k] = join2(nh[k].y, nl[k].y); }
                     if (c4 + 1 < hi4) {
 #pragma unroll
                         for (int k = 0; k < NS; ++k) ldst(k, c4 + 1, nh[k], nl[k]);
                     }
                     tm_wait_ld();
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float b[NS], Aa[NS];
+                    for (int k = 0; k < NS; ++k) { b01[k] = F2(ab[k][0], ab[k][1]); b23[k] = F2(ab[k][2], ab[k][3]); }
+                    act_bwd2<NS>(b01, A01);                   // pad units: abar = 0 and A = 0 -> 0
+                    act_bwd2<NS>(b23, A23);
 #pragma unroll
-                        for (int k = 0; k < NS; ++k) { b[k] = ab[k][u]; Aa[k] = Av[k][u]; }
-                        act_bwd<NS>(b, Aa);                   // pad units: abar = 0 and A = 0 -> 0
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) ab[k][u] = b[k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) put4(nullptr, k, c4, ab[k]);
+                    for (int k = 0; k < NS; ++k) put4(nullptr, k, c4, b01[k], b23[k]);
                 }
                 if (l > 2) {
                     publish_fences();
@@ -771,7 +851,7 @@ extern "C" void pe_debug_set_tcf_profile(unsigned long long* d_counters32) { g_t
 
 // Scratch layout (d_stash of the C ABI): [slots][stash floats per slot] then the operand images.  Per slot: (L-1) layers x 5 streams x
 // F_STREAM bytes (the planes are stashed as they are).
-int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st,
+int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,
                         const pe_term_desc* term2, const float* points2, int n2, const float* aux2) {
     TcfArgs t;
     t.r = a;
@@ -783,6 +863,7 @@ int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int sl
     }
     if (plan->lay.L < 3) { pe_set_error("tcf engine: needs at least two hidden layers"); return 1; }
     t.prof = g_tcf_prof;
+    t.fast = fast;
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
     uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
     t.images = images;

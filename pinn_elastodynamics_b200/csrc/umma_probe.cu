@@ -156,26 +156,35 @@ extern "C" int umma_probe(const void* smem_image, int smem_bytes, const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------- timing
-// One thread issues n_mma MMAs of ONE shape from registers (descriptors advance by constant steps with a period, accumulators rotate),
-// so the loop is a handful of integer adds per MMA: the cycle count is the tensor pipe's time unless the shape is faster than the issue.
+// n_warps issuing warps (1, 2 or 4) each issue n_mma MMAs of ONE shape from registers (descriptors advance by constant steps with a
+// period, accumulators rotate; warp w uses accumulator columns from w * 128), so the loop is a handful of integer adds per MMA: the cycle
+// count is the tensor pipe's time unless the shape is faster than the issue.  uniform = 1: every lane of the issuing warp runs the loop
+// (warp-uniform values, the MMA itself behind elect.sync) instead of lane 0 alone.
 struct TimingArgs {
-    int smem_bytes, n_mma, ts;            // ts: 1 = A operand from tensor memory (column a_col0 + (i % a_period) * a_step)
+    int smem_bytes, n_mma, ts, n_warps, uniform;
     uint32_t idesc;
-    uint64_t a_desc0; uint32_t a_step16; int a_period;     // SS: descriptor start address advances by a_step16 (16-byte units)
+    uint64_t a_desc0; uint32_t a_step16; int a_period;     // SS: descriptor start address advances by a_step16 (16-byte units); TS: TMEM column step
     uint64_t b_desc0; uint32_t b_step16; int b_period;
     uint32_t d_stride; int n_acc;
     long long* cycles;
 };
 
-template <int TS>
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
+    return pred;
+}
+
+template <int TS, int P, int NACC>
 __global__ void __launch_bounds__(128, 1) umma_timing_kernel(TimingArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar[4];
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    __shared__ long long t_end[4], t_issue[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < a.smem_bytes / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;      // fp16 ones
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+        for (int w = 0; w < 4; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[w])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -197,56 +206,80 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(TimingArgs a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {
+    const long long t0 = clock64();
+    if (warp < a.n_warps && (a.uniform || lane == 0)) {
         const uint64_t base16 = (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
         const uint64_t a0 = a.a_desc0 + base16, b0 = a.b_desc0 + base16;
-        const long long t0 = clock64();
-        int ia = 0, ib = 0, id = 0;
-#pragma unroll 4
-        for (int i = 0; i < a.n_mma; ++i) {
-            const uint64_t db = b0 + (uint64_t)(ib * a.b_step16);
-            const uint32_t d = tbase + a.d_stride * id;
-            const uint32_t acc = i >= a.n_acc ? 1u : 0u;
-            if (TS) {
-                const uint32_t ta = tbase + 448u + (uint32_t)(ia * a.a_step16);
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(ta), "l"(db), "r"(a.idesc), "r"(acc) : "memory");
-            } else {
-                const uint64_t da = a0 + (uint64_t)(ia * a.a_step16);
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d), "l"(da), "l"(db), "r"(a.idesc), "r"(acc) : "memory");
+        const uint32_t dbase = tbase + (uint32_t)warp * (a.n_warps > 1 ? 96u : 0u);
+        // the whole period of descriptors and accumulator addresses lives in registers: the unrolled body is a few moves per MMA
+        uint64_t ad[P], bd[P];
+        uint32_t ta[P], dc[NACC];
+#pragma unroll
+        for (int j = 0; j < P; ++j) { ad[j] = a0 + (uint64_t)(j * a.a_step16); bd[j] = b0 + (uint64_t)(j * a.b_step16); ta[j] = tbase + 448u + (uint32_t)(j * a.a_step16); }
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) dc[j] = dbase + a.d_stride * j;
+        constexpr int BODY = P * NACC;                 // one full period of (operand, accumulator) pairs
+        const int reps = a.n_mma / BODY;
+        const uint32_t go = a.uniform ? elect_one() : 1u;
+        if (go) {
+#pragma unroll
+            for (int j = 0; j < BODY; ++j) {           // first period: the accumulators start fresh
+                const uint32_t acc = j >= NACC ? 1u : 0u;
+                if (TS) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(dc[j % NACC]), "r"(ta[j % P]), "l"(bd[j % P]), "r"(a.idesc), "r"(acc) : "memory");
+                else asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(dc[j % NACC]), "l"(ad[j % P]), "l"(bd[j % P]), "r"(a.idesc), "r"(acc) : "memory");
             }
-            if (++ia == a.a_period) ia = 0;
-            if (++ib == a.b_period) ib = 0;
-            if (++id == a.n_acc) id = 0;
+#pragma unroll 1
+            for (int r = 1; r < reps; ++r) {
+#pragma unroll
+                for (int j = 0; j < BODY; ++j) {
+                    if (TS) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(dc[j % NACC]), "r"(ta[j % P]), "l"(bd[j % P]), "r"(a.idesc) : "memory");
+                    else asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(dc[j % NACC]), "l"(ad[j % P]), "l"(bd[j % P]), "r"(a.idesc) : "memory");
+                }
+            }
         }
         const long long t1 = clock64();
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        if (go) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[warp])) : "memory");
         uint32_t ok = 0;
         while (!ok)
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
-        a.cycles[0] = clock64() - t0;
-        a.cycles[1] = t1 - t0;
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(&mbar[warp])), "r"(0) : "memory");
+        if (lane == 0) { t_end[warp] = clock64() - t0; t_issue[warp] = t1 - t0; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) {
+        long long e = 0, is = 0;
+        for (int w = 0; w < a.n_warps; ++w) { e = t_end[w] > e ? t_end[w] : e; is = t_issue[w] > is ? t_issue[w] : is; }
+        a.cycles[0] = e; a.cycles[1] = is;
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
-// returns 0 on success; cycles_out[0] = first issue -> all MMAs complete, cycles_out[1] = issue loop alone
+template <int TS, int P, int NACC>
+static int launch_timing(const TimingArgs& a) {
+    auto k = umma_timing_kernel<TS, P, NACC>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1;
+    k<<<1, 128, a.smem_bytes + 1024, 0>>>(a);
+    return 0;
+}
+
+// returns 0 on success; cycles_out[0] = first issue -> all MMAs complete, cycles_out[1] = issue loop alone (max over the issuing warps);
+// n_mma is per issuing warp
 extern "C" int umma_timing(int smem_bytes, int n_mma, int ts, uint32_t idesc, uint64_t a_desc0, uint32_t a_step16, int a_period,
-                           uint64_t b_desc0, uint32_t b_step16, int b_period, uint32_t d_stride, int n_acc, long long* cycles_out) {
+                           uint64_t b_desc0, uint32_t b_step16, int b_period, uint32_t d_stride, int n_acc, int n_warps, int uniform, long long* cycles_out) {
     TimingArgs a{};
     a.smem_bytes = smem_bytes; a.n_mma = n_mma; a.ts = ts; a.idesc = idesc; a.a_desc0 = a_desc0; a.a_step16 = a_step16; a.a_period = a_period;
-    a.b_desc0 = b_desc0; a.b_step16 = b_step16; a.b_period = b_period; a.d_stride = d_stride; a.n_acc = n_acc;
+    a.b_desc0 = b_desc0; a.b_step16 = b_step16; a.b_period = b_period; a.d_stride = d_stride; a.n_acc = n_acc; a.n_warps = n_warps; a.uniform = uniform;
     void* d_cyc = nullptr;
     CK(cudaMalloc(&d_cyc, 16));
     a.cycles = (long long*)d_cyc;
-    if (ts) {
-        CK(cudaFuncSetAttribute(umma_timing_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        umma_timing_kernel<1><<<1, 128, smem_bytes + 1024, 0>>>(a);
-    } else {
-        CK(cudaFuncSetAttribute(umma_timing_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        umma_timing_kernel<0><<<1, 128, smem_bytes + 1024, 0>>>(a);
-    }
+    // n_mma is rounded down to whole periods of (a_period x n_acc) MMAs; a_period must equal b_period (4 or 8), n_acc 1, 2 or 5
+    int rc = 2;
+    if (a_period == 4 && n_acc == 1) rc = ts ? launch_timing<1, 4, 1>(a) : launch_timing<0, 4, 1>(a);
+    else if (a_period == 4 && n_acc == 2) rc = ts ? launch_timing<1, 4, 2>(a) : launch_timing<0, 4, 2>(a);
+    else if (a_period == 4 && n_acc == 5) rc = ts ? launch_timing<1, 4, 5>(a) : launch_timing<0, 4, 5>(a);
+    else if (a_period == 8 && n_acc == 1) rc = launch_timing<0, 8, 1>(a);
+    else if (a_period == 8 && n_acc == 2) rc = launch_timing<0, 8, 2>(a);
+    if (rc) { snprintf(err, 256, "umma_timing: unsupported period / accumulator combination (%d, %d)", a_period, n_acc); return 1; }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(cycles_out, d_cyc, 16, cudaMemcpyDeviceToHost));

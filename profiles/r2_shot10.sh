@@ -1,0 +1,6 @@
+set +e
+mkdir -p gpurun_out
+rm -f gpurun_out/j_*
+( timeout 400 ncu --set full --clock-control none --import-source on -k regex:resid_tcf -s 3 -c 1 -o gpurun_out/j_tcf_full -f python tests/ncu_target.py tcf 6 ) > gpurun_out/j_ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/j_rc.txt
+( PE_CHECK_ENGINES=tcf,tcf16 timeout 200 python tests/tcf_gpu_check.py f5 f7 ) > gpurun_out/j_check.log 2>&1; echo "check rc=$?" >> gpurun_out/j_rc.txt
+cat gpurun_out/j_rc.txt; tail -3 gpurun_out/j_ncu.log; grep -E "ms_per_step|terms_rel" gpurun_out/j_check.log | cut -c1-400

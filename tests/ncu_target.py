@@ -8,7 +8,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench                                    # noqa: E402  (make_workload only)
-from oracle import ref_torch as R               # noqa: E402  (Xavier arrays only)
+import numpy as np                              # noqa: E402
+from pinn_elastodynamics_b200.models import xavier_init_lists   # noqa: E402
 import pinn_elastodynamics_b200 as pe           # noqa: E402
 
 engine = sys.argv[1] if len(sys.argv) > 1 else 'tcf'
@@ -16,7 +17,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 layers = [3] + 5 * [50] + [5]
 Collo, HOLE = bench.make_workload(50000)
 m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine=engine)
-Ws, bs = R.xavier_params(layers, seed=1111)
+Ws, bs = xavier_init_lists(layers, np.random.default_rng(1111))
 m.uv_net.set_weights(Ws, bs)
 for _ in range(steps):
     m.engine.adam_step(5e-4)

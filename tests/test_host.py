@@ -126,8 +126,8 @@ def test_engine_support_matrix():
         lib.pe_plan_destroy(plan)
         return r
     f5, f7, w100 = [3] + 5 * [50] + [5], [3] + 5 * [50] + [7], [3] + 8 * [100] + [7]
-    assert set(L.ENGINES) == {'simt', 'tc3s', 'tc1s', 'tcf', 'auto'} and L.ENGINES['auto'] == L.ENGINES['tcf']
-    for eng in ('simt', 'tc3s', 'tc1s', 'tcf', 'auto'):
+    assert set(L.ENGINES) == {'simt', 'tc3s', 'tc1s', 'tcf', 'tcf16', 'auto'} and L.ENGINES['auto'] == L.ENGINES['tcf']
+    for eng in ('simt', 'tc3s', 'tc1s', 'tcf', 'tcf16', 'auto'):
         assert sup(f5, L.RES_F5, 5, eng) == 1 and sup(f7, L.RES_F7, 4, eng) == 1
         assert sup(f5, L.RES_TRACTION, 1, eng) == (1 if eng == 'simt' else 0)      # data terms stay on the SIMT engine
         assert sup(f7, L.RES_COLS, 1, eng) == (1 if eng == 'simt' else 0)
