@@ -29,6 +29,7 @@
 //   epilogue warps: wait ACC, DW -> drain both tiles into this CTA's gradient slot -> adjoint of tanh -> Zbar_{l-1} planes -> publish.
 // Reference lines: see pe_simt.cu / pe_device.cuh (the epilogue algebra is shared with the SIMT engine).
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cstring>
 #include "pe_device.cuh"
 #include "pe_tc_common.cuh"
@@ -43,6 +44,7 @@ using namespace pe_tcc;
 static_assert(TCF_EW == 8 || TCF_EW == 12, "TCF_EW: 8 or 12 epilogue warps");
 constexpr int F_EPI = 32 * TCF_EW, F_THREADS = F_EPI + 128;
 constexpr int F_NH = TCF_EW / 4;                  // unit groups per TMEM lane quadrant
+constexpr int F_MAXG = (14 + F_NH - 1) / F_NH;    // 4-unit groups one epilogue thread owns at most (14 per 56-unit plane)
 constexpr int F_CTRL = TCF_EW;                    // index of the control warp
 constexpr int F_CH = 2048;                        // one chunk of 8 units: 128 points x 16 B
 constexpr int F_PLANE = 7 * F_CH;                 // 14,336: 56 units
@@ -63,7 +65,7 @@ constexpr int F_W0 = F_BIAS + PE_MAX_LAYERS * 256;            // [4][64] floats
 constexpr int F_TOTAL = F_W0 + 1024;                          // 229,632
 static_assert(2 * F_IMG <= F_IMG + 2 * F_STREAM, "the forward image double buffer lives inside the reverse-sweep region");
 static_assert(F_TOTAL <= 227 * 1024, "shared memory map exceeds the 227 KB opt-in limit");
-constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SEMPTY = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144;   // byte offsets in F_MISC
+constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SDONE = 80, B_SFREE = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144;   // byte offsets in F_MISC
 constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW tile: 128 lanes x 112; bias tile: 128 lanes x 8)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
@@ -111,6 +113,20 @@ __device__ __forceinline__ f2 tanh2(f2 x) {
     p = __ffma2_rn(p, x2, F2(-1.0f / 3.0f));
     const f2 sm = __ffma2_rn(__fmul2_rn(x, x2), p, x);
     return F2(fabsf(x.x) < 0.3f ? sm.x : b0, fabsf(x.y) < 0.3f ? sm.y : b1);
+}
+
+// second-time-derivative terms of the value stream's adjoint (pe_dev::act_bwd, K = 5) for two units:
+//   zv -= 2 a (s z_tt) abar_tt + 2 (1 - 3 a^2) A_t z_t abar_tt,   s z_tt = a_tt + 2 a A_t z_t,   z_t = A_t / s  (approximate reciprocal, guarded)
+__device__ __forceinline__ f2 tt_terms(f2 a, f2 s, f2 At, f2 Att, f2 btt, f2 zv) {
+    float i0, i1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(s.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(s.y));
+    const f2 zt = __fmul2_rn(At, F2(s.x > 0.f ? i0 : 0.f, s.y > 0.f ? i1 : 0.f));
+    const f2 aAt = __fmul2_rn(a, At);
+    const f2 sztt = __ffma2_rn(__fmul2_rn(aAt, F2(2.f)), zt, Att);
+    zv = __ffma2_rn(__fmul2_rn(__fmul2_rn(a, sztt), F2(-2.f)), btt, zv);
+    const f2 c = F2(fmaf(-3.f * a.x, a.x, 1.f), fmaf(-3.f * a.y, a.y, 1.f));
+    return __ffma2_rn(__fmul2_rn(__fmul2_rn(__fmul2_rn(c, At), zt), F2(-2.f)), btt, zv);
 }
 
 // adjoint of the tanh layer (pe_dev::act_bwd) for two units at once.  A = stashed outputs (a, a_x, ..), ab = adjoints of the
@@ -175,7 +191,8 @@ struct TcfArgs {
     int n2;
     float inv_n2;
     int fast;                   // 1 = 16-bit forward mode: forward layer GEMMs as single fp16 products (adjoint / weight-gradient GEMMs stay fp16 pairs)
-    unsigned long long* prof;   // PROF instantiation: 32 cycle counters (0..15 epilogue thread 0, 16..31 issuer) of CTA 0
+    unsigned long long* prof;   // PROF instantiation: 32 cycle counters (0..15 epilogue thread 0, 16..31 issuer) of CTA prof_cta
+    int prof_cta;               // $PE_PROF_CTA (default 0)
 };
 
 #define TCF_PROF(slot) do { if (PROF) { if (prof_on) { const long long now_ = clock64(); atomicAdd(args.prof + (slot), (unsigned long long)(now_ - prof_t)); prof_t = now_; } } } while (0)
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     const pe_term_desc& T2 = args.term2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = lay.L;
-    const bool prof_on = PROF && args.prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == F_EPI);
+    const bool prof_on = PROF && args.prof != nullptr && (int)blockIdx.x == args.prof_cta && (tid == 0 || tid == F_EPI);
     long long prof_t = 0;
     (void)prof_on; (void)prof_t;
     uint8_t* act = smem + F_ACT;
@@ -244,7 +261,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     const uint32_t act_s = smem_u32(act), r_s = smem_u32(smem + F_R), stg_s = smem_u32(smem + F_STG), ones_s = smem_u32(smem + F_ONES);
     const uint32_t bar0 = smem_u32(smem + F_MISC);
     const uint32_t bar_acc = bar0 + B_ACC, bar_act = bar0 + B_ACT, bar_img = bar0 + B_IMG;
-    const uint32_t bar_sfull = bar0 + B_SFULL, bar_sempty = bar0 + B_SEMPTY, bar_dw = bar0 + B_DW;
+    const uint32_t bar_sfull = bar0 + B_SFULL, bar_sdone = bar0 + B_SDONE, bar_sfree = bar0 + B_SFREE, bar_dw = bar0 + B_DW;
 
     for (int i = tid; i < F_TOTAL / 16; i += F_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int slot = A.slot_base + blockIdx.x;
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     if (tid == 0) {
         for (int g = 0; g < 3; ++g) { mbar_init(bar_acc + 8 * g, 1); mbar_init(bar_act + 8 * g, F_EPI); }
         for (int b = 0; b < 2; ++b) mbar_init(bar_img + 8 * b, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sdone + 8 * b, 1); mbar_init(bar_sfree + 8 * b, F_EPI); }
         mbar_init(bar_dw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -291,7 +308,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         // ============================================================================================ control warpgroup
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         if (warp == F_CTRL && lane == 0) {
-            uint32_t pact = 0, pimg = 0, psfull = 0, psempty = 0;     // parity bits of the phases this thread waits for next
+            uint32_t pact = 0, pimg = 0, psfull = 0, psfree = 0;      // parity bits of the phases this thread waits for next
             uint32_t n_acc2 = 0, n_dw = 0;
             const bool fast = args.fast != 0;
             auto load_fwd = [&](int i) {
@@ -310,6 +327,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
             if (L >= 3) load_fwd(3);
             if (PROF) prof_t = clock64();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                // tiles of the fused primal-only set carry the value stream alone: no MMAs for the derivative streams (their seeds are zero);
+                // the hand-shakes of the other stream groups still happen, with nothing in between
+                const bool sec = tile >= ntiles_main;
                 // ---------------------------------------------------------------- forward: layers 2..L, group by group
                 for (int l = 2; l <= L; ++l) {
                     const uint32_t b = (uint32_t)(l & 1);
@@ -325,6 +345,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                             const uint32_t b_lo = b ? b_lo1 : b_lo0, id = idesc_km(NF);
                             const int ksteps = (lay.d[l - 1] + 15) >> 4;
                             if (g == 0) issue_group<0, 1>(tbase, a_lo, b_lo, km_hi, id, ksteps, fast);
+                            else if (sec) { }
                             else if (g == 1) issue_group<1, 2>(tbase, a_lo, b_lo, km_hi, id, ksteps, fast);
                             else issue_group<3, NS - 3>(tbase, a_lo, b_lo, km_hi, id, ksteps, fast);
                         }
@@ -354,20 +375,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         mbar_expect_tx(bar_sfull + 8 * sb, F_STREAM);
                         tma_load_1d(stg_s + sb * F_STREAM, stash_in + (size_t)k * F_STREAM, F_STREAM, bar_sfull + 8 * sb);
                     };
+                    const int nst = sec ? 1 : NS;               // streams of this tile
                     load_stage(0);                              // both slots are free: the previous layer's DW phase is complete
-                    load_stage(1);
+                    if (!sec) load_stage(1);
                     if (l > 2) {                                // pull the planes of the next (shallower) layer towards L2 while this layer runs
                         const uint8_t* nxt = stash + (size_t)(l - 3) * STASH_LAYER;
 #pragma unroll
                         for (int k = 0; k < NS; ++k)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + (size_t)k * F_STREAM), "r"(F_STREAM) : "memory");
+                            if (k < nst) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + (size_t)k * F_STREAM), "r"(F_STREAM) : "memory");
                     }
                     wait_img(0);
                     TCF_PROF(24);
                     wait_act(0); wait_act(1); wait_act(2);
                     TCF_PROF(25);
                     fence_after();
-                    issue_group<0, NS>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
+                    if (sec) issue_group<0, 1>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
+                    else issue_group<0, NS>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
                     mma_commit(bar_acc);
                     mma_commit(bar_acc + 8);
                     mma_commit(bar_acc + 16);
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
                     const uint32_t id112 = idesc_mn(112), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
 #pragma unroll 1
-                    for (int k = 0; k < NS; ++k) {
+                    for (int k = 0; k < nst; ++k) {
                         const uint32_t sb = (uint32_t)(k & 1);
                         mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
                         psfull ^= 1u << sb;
@@ -398,22 +421,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                                 mma_bf16_ss(tbase + T_DW + 56, da, mk_desc(zl + 16u * s, mn_hi), idz, first);
                             }
                         }
-                        if (k + 2 < NS) mma_commit(bar_sempty + 8 * sb);       // this slot is refilled (stream k + 2) once its MMAs are complete
-                        if (k >= 1 && k + 1 < NS) {                          // ... which is waited for one stream later, behind the next stream's MMAs
+                        if (k == 0) {
+                            // bias gradient: column 0 of  [Zh | Zl]^T 1: the value-stream planes as MN-major A operand (M = 128: rows 0..55 sums
+                            // of Zh, rows 56..111 sums of Zl), a block of ones as B operand (N = 8)
+#pragma unroll
+                            for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_BIAS, mk_desc(z_lo + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
+                        }
+                        mma_commit(bar_sdone + 8 * sb);        // the epilogue warps' pass over stream k starts (staged planes + accumulators -> Zbar_{l-1,k})
+                        if (k >= 1 && k + 1 < nst) {           // slot of stream k - 1: refilled (stream k + 1) once the epilogue warps have read it
                             const uint32_t ob = sb ^ 1u;
-                            mbar_wait(bar_sempty + 8 * ob, (psempty >> ob) & 1u);
-                            psempty ^= 1u << ob;
+                            mbar_wait(bar_sfree + 8 * ob, (psfree >> ob) & 1u);
+                            psfree ^= 1u << ob;
                             load_stage(k + 1);
                         }
                     }
-                    // bias gradient: column 0 of  [Zh | Zl]^T 1: the value-stream planes as MN-major A operand (M = 128: rows 0..55 sums of Zh, rows
-                    // 56..111 sums of Zl), a block of ones as B operand (N = 8)
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_BIAS, mk_desc(z_lo + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
                     mma_commit(bar_dw);
                     ++n_dw;
                     TCF_PROF(27);
-                    mbar_wait(bar_dw, (n_dw - 1) & 1u);      // adjoint image, staging buffers and the Zbar planes are free again
+                    mbar_wait(bar_dw, (n_dw - 1) & 1u);      // every MMA of the layer is complete: the adjoint image is free
+                    mbar_wait(bar_sfree, psfree & 1u);       // ... and so are both staging slots once the last passes of the epilogue warps are through
+                    psfree ^= 1u;
+                    if (!sec) { mbar_wait(bar_sfree + 8, (psfree >> 1) & 1u); psfree ^= 2u; }
                     TCF_PROF(28);
                     if (l > 2) {
                         mbar_expect_tx(bar_img, F_IMG);
@@ -436,7 +464,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         const int p = 32 * (warp & 3) + lane;            // TMEM lane = point of the tile
         const int h = warp >> 2;                         // unit group: 4-unit groups [n4 h / F_NH, n4 (h + 1) / F_NH) of a layer with n4 groups
         const uint32_t tlane = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
-        uint32_t pacc = 0, pdw = 0;
+        uint32_t pacc = 0, pdw = 0, psdone = 0;
         auto wait_acc = [&](int g) { mbar_wait(bar_acc + 8 * g, (pacc >> g) & 1u); pacc ^= 1u << g; };
         auto publish = [&](int g) { mbar_arrive(bar_act + 8 * g); };
         // planes in shared memory were written through the generic proxy and are read next by MMAs (async proxy): a shared-memory proxy fence
@@ -516,7 +544,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         for (int k = 0; k < NS; ++k) o[k][u] = z[k];
                     }
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) put4(stash, k, c4, F2(o[k][0], o[k][1]), F2(o[k][2], o[k][3]));      // stash layer 0 = outputs of layer 1
+                    for (int k = 0; k < NS; ++k)
+                        if (k == 0 || !sec) put4(stash, k, c4, F2(o[k][0], o[k][1]), F2(o[k][2], o[k][3]));      // stash layer 0 = outputs of layer 1
                 }
                 publish_fences();
                 publish(0); publish(1); publish(2);
@@ -547,7 +576,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 TCF_PROF(3);
                 fence_after();
 #pragma unroll 1
-                for (int c4 = lo4; c4 < hi4; ++c4) {
+                for (int c4 = lo4; c4 < (sec ? lo4 : hi4); ++c4) {
                     float z1[4], z2[4];
                     f2 a01, a23;
                     tm_ld4(tlane + T_ACC + 64 + 4 * c4, z1);
@@ -566,7 +595,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 TCF_PROF(5);
                 fence_after();
 #pragma unroll 1
-                for (int c4 = lo4; c4 < hi4; ++c4) {
+                for (int c4 = lo4; c4 < (sec ? lo4 : hi4); ++c4) {
                     float z3[4], z4[4];
                     f2 a01, a23;
                     tm_ld4(tlane + T_ACC + 192 + 4 * c4, z3);
@@ -603,7 +632,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         tm_ld8(tlane + T_ACC + 64 * k, v);
                         tm_wait_ld();
 #pragma unroll
-                        for (int u = 0; u < PE_UJ; ++u) Y[k][u] = (u < 8 && u < dout) ? v[u < 8 ? u : 0] : 0.f;
+                        for (int u = 0; u < PE_UJ; ++u) Y[k][u] = (u < 8 && u < dout && (k == 0 || !sec)) ? v[u < 8 ? u : 0] : 0.f;
                     }
 #pragma unroll
                     for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += bl[u];
@@ -641,10 +670,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 if (h == 0) {
                     // seeds Zbar_L: units 0..7 in groups 0 and 1 (the only chunk the adjoint / weight-gradient MMAs of the output layer use)
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) {
-                        put4(nullptr, k, 0, F2(Y[k][0] * sigma, Y[k][1] * sigma), F2(Y[k][2] * sigma, Y[k][3] * sigma));
-                        put4(nullptr, k, 1, F2(Y[k][4] * sigma, Y[k][5] * sigma), F2(Y[k][6] * sigma, Y[k][7] * sigma));
-                    }
+                    for (int k = 0; k < NS; ++k)
+                        if (k == 0 || !sec) {
+                            put4(nullptr, k, 0, F2(Y[k][0] * sigma, Y[k][1] * sigma), F2(Y[k][2] * sigma, Y[k][3] * sigma));
+                            put4(nullptr, k, 1, F2(Y[k][4] * sigma, Y[k][5] * sigma), F2(Y[k][6] * sigma, Y[k][7] * sigma));
+                        }
                 }
                 publish_fences_global();                     // the whole stash of this tile before the reverse sweep's bulk copies
                 publish(0); publish(1); publish(2);
@@ -654,24 +684,117 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
             for (int l = L; l >= 2; --l) {
                 const int m = l - 1;
                 const int din = lay.d[l - 1], dout = lay.d[l];
-                const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;          // outputs of layer l-1 = inputs A of layer l
                 const int lo4 = c4_lo(din), hi4 = c4_hi(din);
-                // ---- stashed outputs of layer l-1 for this thread's first unit group: in flight while the MMAs run
-                auto ldst = [&](int k, int c4, uint2& hi, uint2& lo) {
-                    const uint8_t* src = stash_in + (size_t)k * F_STREAM + (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
-                    hi = __ldcg(reinterpret_cast<const uint2*>(src));
-                    lo = __ldcg(reinterpret_cast<const uint2*>(src + F_PLANE));
-                };
-                uint2 nh[NS], nl[NS];
-                if (lo4 < hi4) {
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) ldst(k, lo4, nh[k], nl[k]);
-                }
                 wait_acc(0); wait_acc(1); wait_acc(2);       // adjoint MMAs done: abar^{l-1} in the accumulators
                 TCF_PROF(9);
-                mbar_wait(bar_dw, pdw);                      // weight / bias gradient MMAs done: the Zbar_l planes may be overwritten
-                pdw ^= 1u;
+                fence_after();
+                // ---- through tanh of layer l-1, one jet stream at a time, while the weight-gradient phase runs: as soon as the MMAs of stream k are
+                // complete (SDONE) this thread reads its entries of A_{l-1,k} from the staging slot the bulk copy filled -- the stash is read from
+                // L2 once, by the copy -- takes abar_k from tensor memory and overwrites the Zbar_l,k plane (no MMA reads it any more) with
+                // Zbar_{l-1,k}.  The value stream's adjoint needs all streams: a (pass 0) and the running sum  sum_k A_k abar_k  stay in registers,
+                // its plane is written by the last pass (which re-reads A_3 from its slot for the second-time-derivative terms).
+                {
+                    f2 av[F_MAXG][2], acc[F_MAXG][2];
+                    const uint8_t* slot3 = smem + F_STG + F_STREAM;                        // stream 3 lives in slot 3 & 1
+                    if (sec) {                       // primal-only tile: one stream, zbar_0 = s abar_0
+                        mbar_wait(bar_sdone, psdone & 1u);
+                        psdone ^= 1u;
+                        const uint8_t* slot = smem + F_STG;
+#pragma unroll 1
+                        for (int c4 = lo4; c4 < hi4; ++c4) {
+                            const int o = (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
+                            const uint2 hA = *reinterpret_cast<const uint2*>(slot + o), lA = *reinterpret_cast<const uint2*>(slot + F_PLANE + o);
+                            float b0[4];
+                            tm_ld4(tlane + T_ACC + 4 * c4, b0);
+                            const f2 a0 = join2(hA.x, lA.x), a1 = join2(hA.y, lA.y);
+                            const f2 s0 = F2(fmaf(-a0.x, a0.x, 1.f), fmaf(-a0.y, a0.y, 1.f)), s1 = F2(fmaf(-a1.x, a1.x, 1.f), fmaf(-a1.y, a1.y, 1.f));
+                            tm_wait_ld();
+                            put4(nullptr, 0, c4, __fmul2_rn(s0, F2(b0[0], b0[1])), __fmul2_rn(s1, F2(b0[2], b0[3])));
+                        }
+                        mbar_arrive(bar_sfree);
+                        const uint8_t* dead = stash + (size_t)(l - 2) * STASH_LAYER;
+                        for (int i = tid; i < F_STREAM / 128; i += F_EPI)
+                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + (size_t)i * 128) : "memory");
+                    } else
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_wait(bar_sdone + 8 * sb, (psdone >> sb) & 1u);
+                        psdone ^= 1u << sb;
+                        const uint8_t* slot = smem + F_STG + sb * F_STREAM;
+                        // this thread's entries of the slot -> registers, then the slot is released at once (the bulk copy of stream k + 2 is the
+                        // longest link of the per-slot chain copy -> MMAs -> pass; the arithmetic below runs while it is in flight)
+                        // (not in the last pass: nothing waits for its slots within the layer, and it holds the most registers)
+                        const bool EARLY = (k < NS - 1);
+                        uint2 hA[F_MAXG], lA[F_MAXG];
+                        if (EARLY) {
+#pragma unroll
+                            for (int g = 0; g < F_MAXG; ++g) {
+                                const int c4 = lo4 + g;
+                                if (c4 < hi4) {
+                                    const int o = (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
+                                    hA[g] = *reinterpret_cast<const uint2*>(slot + o); lA[g] = *reinterpret_cast<const uint2*>(slot + F_PLANE + o);
+                                }
+                            }
+                            if (!(NS == 5 && k == 3)) mbar_arrive(bar_sfree + 8 * sb);     // stream 3's slot is read again by the last pass
+                        }
+#pragma unroll
+                        for (int g = 0; g < F_MAXG; ++g) {
+                            const int c4 = lo4 + g;
+                            if (c4 < hi4) {
+                                const int o = (c4 >> 1) * F_CH + p * 16 + (c4 & 1) * 8;
+                                if (!EARLY) { hA[g] = *reinterpret_cast<const uint2*>(slot + o); lA[g] = *reinterpret_cast<const uint2*>(slot + F_PLANE + o); }
+                                const f2 A0 = join2(hA[g].x, lA[g].x), A1 = join2(hA[g].y, lA[g].y);
+                                if (k == 0) {
+                                    av[g][0] = A0; av[g][1] = A1;
+                                } else {
+                                    float bk[4], b4[4], b0[4];
+                                    tm_ld4(tlane + T_ACC + 64 * k + 4 * c4, bk);
+                                    if (NS == 5 && k == 3) tm_ld4(tlane + T_ACC + 256 + 4 * c4, b4);
+                                    if (k == NS - 1) tm_ld4(tlane + T_ACC + 4 * c4, b0);
+                                    const f2 a0 = av[g][0], a1 = av[g][1];
+                                    const f2 s0 = F2(fmaf(-a0.x, a0.x, 1.f), fmaf(-a0.y, a0.y, 1.f)), s1 = F2(fmaf(-a1.x, a1.x, 1.f), fmaf(-a1.y, a1.y, 1.f));
+                                    tm_wait_ld();
+                                    const f2 q0 = F2(bk[0], bk[1]), q1 = F2(bk[2], bk[3]);
+                                    if (k == 1) { acc[g][0] = __fmul2_rn(A0, q0); acc[g][1] = __fmul2_rn(A1, q1); }
+                                    else if (k <= 3) { acc[g][0] = __ffma2_rn(A0, q0, acc[g][0]); acc[g][1] = __ffma2_rn(A1, q1, acc[g][1]); }      // s z_k = A_k
+                                    f2 z0 = __fmul2_rn(s0, q0), z1 = __fmul2_rn(s1, q1);
+                                    if (NS == 5 && k == 3) {                              // zbar_t = s abar_t - 4 a A_t abar_tt
+                                        z0 = __ffma2_rn(__fmul2_rn(__fmul2_rn(a0, A0), F2(-4.f)), F2(b4[0], b4[1]), z0);
+                                        z1 = __ffma2_rn(__fmul2_rn(__fmul2_rn(a1, A1), F2(-4.f)), F2(b4[2], b4[3]), z1);
+                                    }
+                                    put4(nullptr, k, c4, z0, z1);
+                                    if (k == NS - 1) {                                    // value stream:  s abar_0 - 2 a sum_k A_k abar_k  [ - tt terms ]
+                                        f2 v0 = __ffma2_rn(__fmul2_rn(a0, acc[g][0]), F2(-2.f), __fmul2_rn(s0, F2(b0[0], b0[1])));
+                                        f2 v1 = __ffma2_rn(__fmul2_rn(a1, acc[g][1]), F2(-2.f), __fmul2_rn(s1, F2(b0[2], b0[3])));
+                                        if (NS == 5) {                                    // here A0 / A1 = a_tt, q0 / q1 = abar_tt
+                                            const uint2 h3 = *reinterpret_cast<const uint2*>(slot3 + o), l3 = *reinterpret_cast<const uint2*>(slot3 + F_PLANE + o);
+                                            v0 = tt_terms(a0, s0, join2(h3.x, l3.x), A0, q0, v0);
+                                            v1 = tt_terms(a1, s1, join2(h3.y, l3.y), A1, q1, v1);
+                                        }
+                                        put4(nullptr, 0, c4, v0, v1);
+                                    }
+                                }
+                            }
+                        }
+                        if (!EARLY) {
+                            if (NS == 5) { mbar_arrive(bar_sfree); mbar_arrive(bar_sfree + 8); }
+                            else mbar_arrive(bar_sfree + 8 * sb);
+                        }
+                        // the stashed planes of stream k have been copied to shared memory and nobody reads them again: drop their (dirty) L2 lines
+                        // instead of letting them be written back to HBM -- the stash is scratch that the next tile overwrites.  Without this the
+                        // whole stash (5.6 KB per point) goes to DRAM and the live part no longer fits L2 (ncu: 286 MB written per 55 k points).
+                        {
+                            const uint8_t* dead = stash + (size_t)(l - 2) * STASH_LAYER + (size_t)k * F_STREAM;
+                            for (int i = tid; i < F_STREAM / 128; i += F_EPI)
+                                asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + (size_t)i * 128) : "memory");
+                        }
+                    }
+                }
                 TCF_PROF(10);
+                mbar_wait(bar_dw, pdw);                      // every weight / bias gradient MMA of the layer is complete
+                pdw ^= 1u;
+                TCF_PROF(11);
                 fence_after();
                 {   // drain.  Tile rows r = 32 * quadrant + lane.  Rows r < din carry Ah^T Zh (columns j) and Ah^T Zl (columns 56 + j) of input unit
                     // i = r; rows 56 <= r < 56 + din carry Al^T Zh of unit i = r - 56.  Two passes with a barrier in between, so that the two adds
@@ -727,28 +850,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         if (r >= 56 && r < 56 + dout) atomicAdd(gB + (r - 56), vb[0] * sc_lo);
                     }
                 }
-                TCF_PROF(11);
-                // ---- through tanh of layer l-1: zbar^{l-1} from abar^{l-1} (TMEM) and the stashed outputs (hi + lo)
-#pragma unroll 1
-                for (int c4 = lo4; c4 < hi4; ++c4) {
-                    float ab[NS][4];
-                    f2 A01[NS], A23[NS], b01[NS], b23[NS];
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) tm_ld4(tlane + T_ACC + 64 * k + 4 * c4, ab[k]);
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) { A01[k] = join2(nh[k].x, nl[k].x); A23[k] = join2(nh[k].y, nl[k].y); }
-                    if (c4 + 1 < hi4) {
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) ldst(k, c4 + 1, nh[k], nl[k]);
-                    }
-                    tm_wait_ld();
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) { b01[k] = F2(ab[k][0], ab[k][1]); b23[k] = F2(ab[k][2], ab[k][3]); }
-                    act_bwd2<NS>(b01, A01);                   // pad units: abar = 0 and A = 0 -> 0
-                    act_bwd2<NS>(b23, A23);
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) put4(nullptr, k, c4, b01[k], b23[k]);
-                }
                 if (l > 2) {
                     publish_fences();
                     publish(0); publish(1); publish(2);
@@ -771,7 +872,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                             const uint8_t* q = base + k * F_STREAM + pp * 16;
                             return fmaf(__half2float(*reinterpret_cast<const __half*>(q + F_PLANE)), LO_INV, __half2float(*reinterpret_cast<const __half*>(q)));
                         };
-                        const float zv = val(0), zx = val(1), zy = val(2), zt = val(3);
+                        const float zv = val(0), zx = sec ? 0.f : val(1), zy = sec ? 0.f : val(2), zt = sec ? 0.f : val(3);
                         g0 = fmaf(c4v.x, zv, fmaf(Tc.in_scale[0], zx, g0));
                         g1 = fmaf(c4v.y, zv, fmaf(Tc.in_scale[1], zy, g1));
                         g2 = fmaf(c4v.z, zv, fmaf(Tc.in_scale[2], zt, g2));
@@ -863,6 +964,7 @@ int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int fa
     }
     if (plan->lay.L < 3) { pe_set_error("tcf engine: needs at least two hidden layers"); return 1; }
     t.prof = g_tcf_prof;
+    { const char* e = getenv("PE_PROF_CTA"); t.prof_cta = e ? atoi(e) : 0; }
     t.fast = fast;
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
     uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);

@@ -544,8 +544,8 @@ class DeepHPM(_Base):
         if self.verbose:
             print('{} th iterations, Loss: {}'.format(self.count, loss))
 
-    def train(self, iter, learning_rate, batch_num):
-        r = self._adam_loop(iter, learning_rate, self._chunks(batch_num))
+    def train(self, iter, learning_rate, batch_num, refeed=False):
+        r = self._adam_loop(iter, learning_rate, self._chunks(batch_num), refeed=refeed)
         return r['loss_f_uv'], r['loss_f_s'], r['loss_IC'], r['loss_SRC'], r['loss']
 
     def train_bfgs(self, batch_num, options=None):
@@ -600,8 +600,8 @@ class DeepElasticWave(_Base):
             raise UnboundLocalError("local variable 'uv_weights' referenced before assignment")
         self._save(self.uv_net, fileDir, TYPE + ' ')
 
-    def train(self, iter, learning_rate, batch_num):
-        r = self._adam_loop(iter, learning_rate, self._chunks(batch_num))
+    def train(self, iter, learning_rate, batch_num, refeed=False):
+        r = self._adam_loop(iter, learning_rate, self._chunks(batch_num), refeed=refeed)
         return r['loss_f_uv'], r['loss_f_s'], r['loss']
 
     def train_bfgs(self, batch_num, options=None):
