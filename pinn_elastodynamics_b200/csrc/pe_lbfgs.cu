@@ -61,6 +61,56 @@ __global__ void __launch_bounds__(LB_T, 1) lbfgs_direction_kernel(int n, int m, 
     for (int i = tid; i < n; i += LB_T) d[i] = -d[i];
 }
 
+// Same recursion with the direction vector held in REGISTERS (n <= EPT * LB_T = 12,288: the 5x50 nets; 1,024 threads leave 64 registers each,
+// wider nets use the kernel above): thread t owns elements t + LB_T * e.  Per pair the two
+// history rows are fetched up front (coalesced, all loads in flight), so a step costs one L2 round trip + one block reduction instead of
+// three passes over d in global memory.  Same summation order per thread and the same block reduction as the kernel above.
+template <int EPT>
+__global__ void __launch_bounds__(LB_T, 1) lbfgs_direction_reg_kernel(int n, int m, int count, int head, const float* __restrict__ g,
+                                                                     const float* __restrict__ S, const float* __restrict__ Y,
+                                                                     const float* __restrict__ state, float* __restrict__ d) {
+    __shared__ double red[LB_T / 32];
+    __shared__ double alpha[64];
+    const int tid = threadIdx.x;
+    float dv[EPT], sv[EPT], yv[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) { const int i = tid + LB_T * e; dv[e] = i < n ? g[i] : 0.f; }
+    for (int j = 0; j < count; ++j) {                    // newest -> oldest
+        const int slot = (head - j + m) % m;
+        const float* s = S + (size_t)slot * n;
+        const float* y = Y + (size_t)slot * n;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) { const int i = tid + LB_T * e; sv[e] = i < n ? __ldcg(s + i) : 0.f; yv[e] = i < n ? __ldcg(y + i) : 0.f; }
+        double p = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) p += (double)sv[e] * (double)dv[e];
+        const double a = (double)state[1 + slot] * block_sum(p, red);
+        if (tid == 0) alpha[j] = a;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) dv[e] = (float)((double)dv[e] - a * (double)yv[e]);
+    }
+    const float gamma = count > 0 ? state[0] : 1.0f;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) dv[e] *= gamma;
+    __syncthreads();
+    for (int j = count - 1; j >= 0; --j) {               // oldest -> newest
+        const int slot = (head - j + m) % m;
+        const float* s = S + (size_t)slot * n;
+        const float* y = Y + (size_t)slot * n;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) { const int i = tid + LB_T * e; sv[e] = i < n ? __ldcg(s + i) : 0.f; yv[e] = i < n ? __ldcg(y + i) : 0.f; }
+        double p = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) p += (double)yv[e] * (double)dv[e];
+        const double b = (double)state[1 + slot] * block_sum(p, red);
+        const double c = alpha[j] - b;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) dv[e] = (float)((double)dv[e] + c * (double)sv[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) { const int i = tid + LB_T * e; if (i < n) d[i] = -dv[e]; }
+}
+
 // s = x - x_prev, y = g - g_prev into slot `head`; rho, gamma and y.s into state.  state[1 + m] = y.s, state[2 + m] = y.y.
 __global__ void __launch_bounds__(LB_T, 1) lbfgs_store_pair_kernel(int n, int m, int head, const float* __restrict__ x, const float* __restrict__ xp,
                                                                   const float* __restrict__ g, const float* __restrict__ gp,
@@ -115,7 +165,8 @@ __global__ void __launch_bounds__(LB_T, 1) dot_max_kernel(int n, const float* __
 extern "C" int pe_lbfgs_direction(int n, int m, int count, int head, const float* d_g, const float* d_S, const float* d_Y,
                                   const float* d_state, float* d_dir, void* stream) {
     if (n < 1 || m < 1 || m > 64 || count < 0 || count > m) { pe_set_error("pe_lbfgs_direction: bad sizes (m <= 64)"); return 1; }
-    lbfgs_direction_kernel<<<1, LB_T, 0, (cudaStream_t)stream>>>(n, m, count, head, d_g, d_S, d_Y, d_state, d_dir);
+    if (n <= 12 * LB_T) lbfgs_direction_reg_kernel<12><<<1, LB_T, 0, (cudaStream_t)stream>>>(n, m, count, head, d_g, d_S, d_Y, d_state, d_dir);
+    else lbfgs_direction_kernel<<<1, LB_T, 0, (cudaStream_t)stream>>>(n, m, count, head, d_g, d_S, d_Y, d_state, d_dir);
     LB_CHECK("lbfgs_direction_kernel");
     return 0;
 }

@@ -41,6 +41,12 @@ using namespace pe_tcc;
 #ifndef TCF_EW
 #define TCF_EW 12
 #endif
+// TCF_ISSUERS = 2: a second issuing thread (lane 0 of the next control warp) drives the weight / bias gradient phase of the reverse sweep
+// -- bulk copies of the stash, its MMAs, the slot hand-shakes -- while the first one issues the adjoint MMAs: one thread's tcgen05.mma
+// issue costs ~64 cycles per instruction, two threads together reach ~40 (tests/probe_umma_timing.py).
+#ifndef TCF_ISSUERS
+#define TCF_ISSUERS 2
+#endif
 static_assert(TCF_EW == 8 || TCF_EW == 12, "TCF_EW: 8 or 12 epilogue warps");
 constexpr int F_EPI = 32 * TCF_EW, F_THREADS = F_EPI + 128;
 constexpr int F_NH = TCF_EW / 4;                  // unit groups per TMEM lane quadrant
@@ -65,7 +71,7 @@ constexpr int F_W0 = F_BIAS + PE_MAX_LAYERS * 256;            // [4][64] floats
 constexpr int F_TOTAL = F_W0 + 1024;                          // 229,632
 static_assert(2 * F_IMG <= F_IMG + 2 * F_STREAM, "the forward image double buffer lives inside the reverse-sweep region");
 static_assert(F_TOTAL <= 227 * 1024, "shared memory map exceeds the 227 KB opt-in limit");
-constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SDONE = 80, B_SFREE = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144;   // byte offsets in F_MISC
+constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SDONE = 80, B_SFREE = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144, B_DRAINED = 160, B_REVGO = 168, B_REVDONE = 176;   // byte offsets in F_MISC
 constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW tile: 128 lanes x 112; bias tile: 128 lanes x 8)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     const pe_term_desc& T2 = args.term2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = lay.L;
-    const bool prof_on = PROF && args.prof != nullptr && (int)blockIdx.x == args.prof_cta && (tid == 0 || tid == F_EPI);
+    const bool prof_on = PROF && args.prof != nullptr && (int)blockIdx.x == args.prof_cta && (tid == 0 || tid == F_EPI || (TCF_ISSUERS == 2 && tid == F_EPI + 32));
     long long prof_t = 0;
     (void)prof_on; (void)prof_t;
     uint8_t* act = smem + F_ACT;
@@ -261,7 +267,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     const uint32_t act_s = smem_u32(act), r_s = smem_u32(smem + F_R), stg_s = smem_u32(smem + F_STG), ones_s = smem_u32(smem + F_ONES);
     const uint32_t bar0 = smem_u32(smem + F_MISC);
     const uint32_t bar_acc = bar0 + B_ACC, bar_act = bar0 + B_ACT, bar_img = bar0 + B_IMG;
-    const uint32_t bar_sfull = bar0 + B_SFULL, bar_sdone = bar0 + B_SDONE, bar_sfree = bar0 + B_SFREE, bar_dw = bar0 + B_DW;
+    const uint32_t bar_sfull = bar0 + B_SFULL, bar_sdone = bar0 + B_SDONE, bar_sfree = bar0 + B_SFREE, bar_dw = bar0 + B_DW, bar_drained = bar0 + B_DRAINED;
+    const uint32_t bar_revgo = bar0 + B_REVGO, bar_revdone = bar0 + B_REVDONE;
 
     for (int i = tid; i < F_TOTAL / 16; i += F_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int slot = A.slot_base + blockIdx.x;
@@ -287,6 +294,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         for (int b = 0; b < 2; ++b) mbar_init(bar_img + 8 * b, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sdone + 8 * b, 1); mbar_init(bar_sfree + 8 * b, F_EPI); }
         mbar_init(bar_dw, 1);
+        mbar_init(bar_drained, F_EPI);
+        mbar_init(bar_revgo, 1); mbar_init(bar_revdone, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == F_CTRL) {
@@ -309,6 +318,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         if (warp == F_CTRL && lane == 0) {
             uint32_t pact = 0, pimg = 0, psfull = 0, psfree = 0;      // parity bits of the phases this thread waits for next
+            uint32_t pdrained = 1;                                    // ... of the PREVIOUS drain: the first wait passes on the fresh barrier
+            uint32_t prevdone = 0;
+            (void)pdrained; (void)prevdone; (void)psfull; (void)psfree;
             uint32_t n_acc2 = 0, n_dw = 0;
             const bool fast = args.fast != 0;
             auto load_fwd = [&](int i) {
@@ -366,6 +378,35 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
                 mbar_expect_tx(bar_img, F_IMG);
                 tma_load_1d(r_s, adj_src(L), F_IMG, bar_img);
+#if TCF_ISSUERS == 2
+                mbar_arrive(bar_revgo);                      // the second issuer may start this tile's gradient phases (the staging slots are free)
+                for (int l = L; l >= 2; --l) {
+                    const int dout = lay.d[l];
+                    wait_img(0);
+                    TCF_PROF(24);
+                    wait_act(0); wait_act(1); wait_act(2);
+                    TCF_PROF(25);
+                    fence_after();
+                    if (sec) issue_group<0, 1>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
+                    else issue_group<0, NS>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
+                    mma_commit(bar_acc);
+                    mma_commit(bar_acc + 8);
+                    mma_commit(bar_acc + 16);
+                    ++n_acc2;
+                    TCF_PROF(26);
+                    if (l > 2) {                             // the adjoint image is free once this layer's adjoint MMAs are complete
+                        mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
+                        mbar_expect_tx(bar_img, F_IMG);
+                        tma_load_1d(r_s, adj_src(l - 1), F_IMG, bar_img);
+                    }
+                }
+                mbar_wait(bar_revdone, prevdone);            // every gradient MMA of the tile is complete and both staging slots are free
+                prevdone ^= 1u;
+                if (tile + (int)gridDim.x < ntiles) {
+                    load_fwd(2);
+                    if (L >= 3) load_fwd(3);
+                }
+#else
                 for (int l = L; l >= 2; --l) {
                     const int dout = lay.d[l];
                     const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;     // outputs of layer l-1 = inputs A of layer l
@@ -401,6 +442,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     //      ignored); the B operand [Zh | Zl] (N = 112).  Tile: rows i, columns j: Ah^T Zh | rows i, columns 56 + j: Ah^T Zl | rows 56 + i,
                     //      columns j: Al^T Zh (the cross products carry 2^11 and are resolved when the tile is drained).  The MMA count, not the MMA
                     //      size, is what the tensor pipe charges for at these shapes (tests/probe_umma_timing.py: ~64 cycles per instruction up to N = 128).
+                    // the gradient tiles of the previous layer (or tile) must have been drained before they are overwritten; the epilogue warps
+                    // publish Zbar first and drain afterwards, behind the adjoint MMAs issued above
+                    mbar_wait(bar_drained, pdrained);
+                    pdrained ^= 1u;
                     const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
                     const uint32_t id112 = idesc_mn(112), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
 #pragma unroll 1
@@ -451,8 +496,100 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         if (L >= 3) load_fwd(3);
                     }
                 }
+#endif
             }
         }
+#if TCF_ISSUERS == 2
+        else if (warp == F_CTRL + 1 && lane == 0) {
+            // ---------------------------------------------------------------- second issuer: weight / bias gradient phases of the reverse sweep
+            uint32_t pact = 0, psfull = 0, psfree = 0, pdrained = 1, prevgo = 0, n_dw = 0;
+            auto wait_act = [&](int g) { mbar_wait(bar_act + 8 * g, (pact >> g) & 1u); pact ^= 1u << g; };
+            const uint32_t mn_hi = desc_hi(F_CH);
+            const uint32_t z_lo = desc_lo(act_s, 128), g_lo = desc_lo(stg_s, 128);
+            const uint64_t d_ones = mk_desc(desc_lo(ones_s, 128), desc_hi(256));
+            if (PROF) prof_t = clock64();
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const bool sec = tile >= ntiles_main;
+                // the L - 1 phases of every ACT barrier that belong to the forward sweep (layers 2..L) are the first issuer's
+                if ((L - 1) & 1) pact ^= 7u;
+                mbar_wait(bar_revgo, prevgo);                // forward MMAs complete: the region F_R changes hands
+                prevgo ^= 1u;
+                for (int l = L; l >= 2; --l) {
+                    const int dout = lay.d[l];
+                    const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;     // outputs of layer l-1 = inputs A of layer l
+                    // the stashed planes of A_{l-1} come back one stream (hi plane | lo plane, 28,672 B) per bulk copy into two staging slots
+                    auto load_stage = [&](int k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_expect_tx(bar_sfull + 8 * sb, F_STREAM);
+                        tma_load_1d(stg_s + sb * F_STREAM, stash_in + (size_t)k * F_STREAM, F_STREAM, bar_sfull + 8 * sb);
+                    };
+                    const int nst = sec ? 1 : NS;               // streams of this tile
+                    load_stage(0);                              // both slots are free: the previous layer's DW phase is complete
+                    if (!sec) load_stage(1);
+                    if (l > 2) {                                // pull the planes of the next (shallower) layer towards L2 while this layer runs
+                        const uint8_t* nxt = stash + (size_t)(l - 3) * STASH_LAYER;
+#pragma unroll
+                        for (int k = 0; k < NS; ++k)
+                            if (k < nst) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + (size_t)k * F_STREAM), "r"(F_STREAM) : "memory");
+                    }
+                    wait_act(0); wait_act(1); wait_act(2);
+                    fence_after();
+                    // ---- weight gradient  dW = sum_k A_k^T Zbar_k  (K = 128 points, 8 K-steps of 16) as ONE M = 128 MMA per K-step: the A operand is
+                    //      the staged stream read MN-major, rows 0..55 = Ah units, rows 56..111 = Al units (rows 112..127: whatever follows the slot,
+                    //      ignored); the B operand [Zh | Zl] (N = 112).  Tile: rows i, columns j: Ah^T Zh | rows i, columns 56 + j: Ah^T Zl | rows 56 + i,
+                    //      columns j: Al^T Zh (the cross products carry 2^11 and are resolved when the tile is drained).  The MMA count, not the MMA
+                    //      size, is what the tensor pipe charges for at these shapes (tests/probe_umma_timing.py: ~64 cycles per instruction up to N = 128).
+                    // the gradient tiles of the previous layer (or tile) must have been drained before they are overwritten; the epilogue warps
+                    // publish Zbar first and drain afterwards, behind the adjoint MMAs issued above
+                    mbar_wait(bar_drained, pdrained);
+                    pdrained ^= 1u;
+                    const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
+                    const uint32_t id112 = idesc_mn(112), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
+#pragma unroll 1
+                    for (int k = 0; k < nst; ++k) {
+                        const uint32_t sb = (uint32_t)(k & 1);
+                        mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
+                        psfull ^= 1u << sb;
+                        const uint32_t ga = g_lo + sb * (uint32_t)(F_STREAM >> 4);
+                        const uint32_t zh = z_lo + (uint32_t)k * (uint32_t)(F_STREAM >> 4), zl = zh + (uint32_t)(F_PLANE >> 4);
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {                        // K-steps of 16 points = 256 B
+                            const uint64_t da = mk_desc(ga + 16u * s, mn_hi);
+                            const uint32_t first = (k > 0 || s > 0) ? 1u : 0u;
+                            if (nzc == 7) {                                  // the two Z planes are contiguous: one N = 112 MMA
+                                mma_bf16_ss(tbase + T_DW, da, mk_desc(zh + 16u * s, mn_hi), id112, first);
+                            } else {
+                                mma_bf16_ss(tbase + T_DW, da, mk_desc(zh + 16u * s, mn_hi), idz, first);
+                                mma_bf16_ss(tbase + T_DW + 56, da, mk_desc(zl + 16u * s, mn_hi), idz, first);
+                            }
+                        }
+                        if (k == 0) {
+                            // bias gradient: column 0 of  [Zh | Zl]^T 1: the value-stream planes as MN-major A operand (M = 128: rows 0..55 sums
+                            // of Zh, rows 56..111 sums of Zl), a block of ones as B operand (N = 8)
+#pragma unroll
+                            for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_BIAS, mk_desc(z_lo + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
+                        }
+                        mma_commit(bar_sdone + 8 * sb);        // the epilogue warps' pass over stream k starts (staged planes + accumulators -> Zbar_{l-1,k})
+                        if (k >= 1 && k + 1 < nst) {           // slot of stream k - 1: refilled (stream k + 1) once the epilogue warps have read it
+                            const uint32_t ob = sb ^ 1u;
+                            mbar_wait(bar_sfree + 8 * ob, (psfree >> ob) & 1u);
+                            psfree ^= 1u << ob;
+                            load_stage(k + 1);
+                        }
+                    }
+                    mma_commit(bar_dw);
+                    ++n_dw;
+                    TCF_PROF(27);
+                    mbar_wait(bar_dw, (n_dw - 1) & 1u);      // every MMA of the layer is complete: the adjoint image is free
+                    mbar_wait(bar_sfree, psfree & 1u);       // ... and so are both staging slots once the last passes of the epilogue warps are through
+                    psfree ^= 1u;
+                    if (!sec) { mbar_wait(bar_sfree + 8, (psfree >> 1) & 1u); psfree ^= 2u; }
+                    TCF_PROF(28);
+                }
+                mbar_arrive(bar_revdone);
+            }
+        }
+#endif
         __syncwarp();
     } else {
         // ============================================================================================ epilogue warps
@@ -792,6 +929,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     }
                 }
                 TCF_PROF(10);
+                if (l > 2) {                                 // Zbar_{l-1} is complete: the next layer's adjoint MMAs may start while the tiles are drained
+                    publish_fences();
+                    publish(0); publish(1); publish(2);
+                }
                 mbar_wait(bar_dw, pdw);                      // every weight / bias gradient MMA of the layer is complete
                 pdw ^= 1u;
                 TCF_PROF(11);
@@ -850,10 +991,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                         if (r >= 56 && r < 56 + dout) atomicAdd(gB + (r - 56), vb[0] * sc_lo);
                     }
                 }
-                if (l > 2) {
-                    publish_fences();
-                    publish(0); publish(1); publish(2);
-                }
+                fence_before();
+                mbar_arrive(bar_drained);                    // the issuer may overwrite the gradient tiles
                 TCF_PROF(12);
             }
             // ================================================================ layer 1 gradient (3 x d1 + bias): FFMA, fixed-order reduce

@@ -137,6 +137,13 @@ def shard_range(n, rank, world):
     return int(rank * n / world), int((rank + 1) * n / world)
 
 
+def chunk_shard_range(g_lo, g_hi, rank, world):
+    """GLOBAL rows of rank `rank` inside the batch_num chunk [g_lo, g_hi): the chunk itself is index-sharded over all ranks, so every
+    GPU works on every chunk (the reference trains the chunks one after the other on one device, semi:299-305)."""
+    a, b = shard_range(g_hi - g_lo, rank, world)
+    return g_lo + a, g_lo + b
+
+
 class LossEngine:
     """Loss terms + gradient of one trainable network on one rank."""
 
@@ -208,8 +215,8 @@ class LossEngine:
             # living on the ranks whose resident shard happens to contain it; one H2D copy per chunk switch (once per `iter` steps)
             if term.aux is not None:
                 raise L.PeError('batch_num chunking of a composite (aux) point set with world_size > 1 is not supported')
-            a, b = shard_range(g_hi - g_lo, self.rank, self.world)
-            term.points = torch.from_numpy(term.host[g_lo + a:g_lo + b]).to(self.device)
+            a, b = chunk_shard_range(g_lo, g_hi, self.rank, self.world)
+            term.points = torch.from_numpy(term.host[a:b]).to(self.device)
             term.lo, term.hi = 0, b - a
             term.desc.n_global = g_hi - g_lo
         self._built = False

@@ -24,16 +24,21 @@ def cubic_min(a, fa, da, b, fb, db):
     return b - (b - a) * (db + d2 - d1) / den
 
 
-def strong_wolfe(phi, f0, dphi0, alpha, c1=1e-3, c2=0.9, maxls=20, budget=None):
+def strong_wolfe(phi, f0, dphi0, alpha, c1=1e-3, c2=0.9, maxls=20, budget=None, first=None):
     """phi(alpha) -> (f, dphi, aux).  Returns (ok, alpha, f, dphi, aux); when ok, the LAST phi call was made at the returned
-    alpha (the device state is left there).  budget() -> evaluations still allowed (maxfun), or None."""
+    alpha (the device state is left there).  budget() -> evaluations still allowed (maxfun), or None.
+    first = (f, dphi, aux): the result of phi(alpha) at the initial trial step when the caller has evaluated it already
+    (the device-resident driver queues the first trial behind the direction kernel without a host round trip)."""
     a_lo, f_lo, d_lo = 0.0, f0, dphi0
     a_hi = f_hi = d_hi = None
     last = None
     for ls in range(maxls):
         if budget is not None and budget() <= 0 and last is not None:
             break
-        fa, da, aux = phi(alpha)
+        if ls == 0 and first is not None:
+            fa, da, aux = first
+        else:
+            fa, da, aux = phi(alpha)
         last = (alpha, fa, da, aux)
         if not math.isfinite(fa):                                      # stepped out of the representable region: pull back
             a_hi, f_hi, d_hi = alpha, math.inf, None

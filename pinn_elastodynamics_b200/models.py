@@ -20,6 +20,7 @@ import os
 import pickle
 
 import numpy as np
+import scipy.optimize          # L-BFGS-B driver of train_bfgs (imported here: ~0.4 s the first time, not inside the optimisation call)
 import torch
 
 from . import _lib as L
@@ -196,7 +197,6 @@ class _Base:
     def _bfgs(self, options, callback, engine=None, net=None, total=None, shown=None, driver=None):
         """total(terms) is the minimised scalar; shown(terms) is what the reference passes to loss_callback
         (`fetches`, e.g. the unscaled loss_DIST while 1000*loss_DIST is minimised, plate:220,543)."""
-        import scipy.optimize
         engine = engine or self.engine
         net = net or self.uv_net
         total = total or self._total
@@ -230,7 +230,6 @@ class _Base:
         a strong-Wolfe line search (sufficient decrease 1e-3, curvature 0.9: the constants of L-BFGS-B's lnsrlb).
         Honours maxiter / maxfun / maxcor / maxls / ftol / gtol with SciPy's meaning and returns an OptimizeResult.
         Iterates are not bit-identical to SciPy's (different line search, fp32 vectors); tests compare the reached loss."""
-        import scipy.optimize
         lib, n, dev = engine.lib, net.Pp, self.device
         m = max(1, min(int(options.get('maxcor', 10)), 64))
         maxiter = int(options.get('maxiter', 15000)); maxfun = int(options.get('maxfun', 15000))
@@ -267,6 +266,30 @@ class _Base:
             L.check(lib.pe_vec_axpy(n, P(x), P(xprev), float(alpha), P(d), st()), 'pe_vec_axpy')
             return feval(d)
 
+        scal2 = torch.zeros(12, **f32)
+        import time as _time
+        trace = {'enqueue': 0.0, 'sync': 0.0, 'n': 0} if os.environ.get('PE_BFGS_TRACE') else None
+
+        def step_and_eval(alpha0):
+            """direction is in d: queue  g.d -> save x, g -> x = x + alpha0 d -> evaluate -> g_new.d  and read everything back with ONE
+            device->host copy: (dphi0, f(alpha0), dphi(alpha0), max|g_new|)."""
+            nonlocal nfev
+            L.check(lib.pe_vec_dot_max(n, P(g), P(d), P(scal2[10:]), st()), 'pe_vec_dot_max')
+            xprev.copy_(x); gprev.copy_(g)
+            L.check(lib.pe_vec_axpy(n, P(x), P(xprev), float(alpha0), P(d), st()), 'pe_vec_axpy')
+            engine.evaluate()
+            nfev += 1
+            scal2[:8].copy_(engine.out[n:n + 8])
+            L.check(lib.pe_vec_dot_max(n, P(g), P(d), P(scal2[8:10]), st()), 'pe_vec_dot_max')
+            if trace is not None:
+                t1 = _time.perf_counter()
+            h = scal2.cpu().numpy().astype(np.float64)
+            if trace is not None:
+                t2 = _time.perf_counter()
+                trace['enqueue'] += t1 - trace.get('t0', t1); trace['sync'] += t2 - t1; trace['n'] += 1
+            callback(shown(h[:8]))
+            return float(h[10]), (total(h[:8]), float(h[8]), float(h[9]))
+
         f, gg, gmax = feval(g)
         count, head, nit = 0, -1, 0
         message, success = 'STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT', False
@@ -277,18 +300,22 @@ class _Base:
             if nfev >= maxfun:
                 message = 'STOP: TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT'
                 break
+            if trace is not None:
+                trace['t0'] = _time.perf_counter()
             L.check(lib.pe_lbfgs_direction(n, m, count, max(head, 0), P(g), P(S), P(Y), P(state), P(d), st()), 'pe_lbfgs_direction')
-            _, dphi0, _ = scalars(d)
+            alpha0 = 1.0 if count > 0 else min(1.0, 1.0 / max(np.sqrt(gg), 1e-30))   # L-BFGS-B: first step 1/||d||
+            # the first trial point of the line search is evaluated right behind the direction kernel: one host round trip per iteration
+            # in the common case (unit step accepted) instead of one per kernel result the host looks at
+            dphi0, first = step_and_eval(alpha0)
             if not dphi0 < 0.0:
+                x.copy_(xprev); g.copy_(gprev)                          # the speculative step is void
                 if count == 0:
                     message = 'ABNORMAL: NOT A DESCENT DIRECTION'
                     break
                 count = 0                                               # drop the history, restart from steepest descent
                 _, gg, gmax = scalars(g)                                # ... whose first trial step is 1 / ||g|| of the CURRENT gradient
                 continue
-            xprev.copy_(x); gprev.copy_(g)
-            alpha0 = 1.0 if count > 0 else min(1.0, 1.0 / max(np.sqrt(gg), 1e-30))   # L-BFGS-B: first step 1/||d||
-            ok, alpha, f_new, _, gmax_new = strong_wolfe(phi, f, dphi0, alpha0, c1, c2, maxls, budget=lambda: maxfun - nfev)
+            ok, alpha, f_new, _, gmax_new = strong_wolfe(phi, f, dphi0, alpha0, c1, c2, maxls, budget=lambda: maxfun - nfev, first=first)
             if not ok:
                 x.copy_(xprev); g.copy_(gprev)
                 if nfev >= maxfun:
@@ -309,6 +336,9 @@ class _Base:
             if rel <= ftol:
                 message, success = 'CONVERGENCE: RELATIVE REDUCTION OF F <= FTOL', True
                 break
+        if trace is not None and trace['n']:
+            import sys as _sys
+            print('[bfgs trace] iterations %d: host enqueue %.3f ms, wait for the device %.3f ms per iteration' % (trace['n'], 1e3 * trace['enqueue'] / trace['n'], 1e3 * trace['sync'] / trace['n']), file=_sys.stderr)
         return scipy.optimize.OptimizeResult(x=net.get_flat().astype(np.float64), fun=f, nit=nit, nfev=nfev, message=message,
                                              success=success, status=0 if success else 1)
 

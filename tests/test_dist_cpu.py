@@ -91,3 +91,17 @@ def test_two_rank_sharded_training_equals_single_rank():
         orc.adam_step(gs, 5e-4)
     np.testing.assert_allclose(res[0][1], ref_curve, rtol=1e-12)
     np.testing.assert_allclose(res[0][0], orc.flat_params(), rtol=1e-10, atol=1e-14)
+
+
+def test_chunks_are_sharded_over_all_ranks():
+    """batch_num chunking under world_size > 1 (engine.set_chunk): the ranks' parts of a chunk tile it exactly, in rank order, for ragged
+    sizes too; with one rank the part is the chunk itself"""
+    from pinn_elastodynamics_b200.engine import chunk_shard_range
+    for N, B, world in ((2003, 3, 2), (150357, 7, 8), (10, 4, 8), (5, 1, 3)):
+        for i in range(B):
+            g_lo, g_hi = int(i * N / B), int((i + 1) * N / B)                 # semi:300-302
+            parts = [chunk_shard_range(g_lo, g_hi, r, world) for r in range(world)]
+            assert parts[0][0] == g_lo and parts[-1][1] == g_hi
+            assert all(a <= b for a, b in parts) and all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+        assert chunk_shard_range(3, 11, 0, 1) == (3, 11)
