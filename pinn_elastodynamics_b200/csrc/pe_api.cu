@@ -2,6 +2,7 @@
 // entry point replaces).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "pe_common.cuh"
@@ -13,6 +14,11 @@ void pe_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pe_pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PE_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 int pe_launch_resid_tcs(const pe_plan* plan, const PeResidArgs& a, int K, int fast, int slots, cudaStream_t st,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/pinn_elasto.h"
 
 #define PE_P 32          // points per tile (lane = point)
@@ -66,6 +67,28 @@ static __host__ __device__ inline int pe_lda(int d) {
 }
 
 void pe_set_error(const char* fmt, ...);
+
+// ---- programmatic dependent launch (PDL).  The Adam step is three back-to-back kernels on one stream (operand images -> residual ->
+// slot reduction + Adam); launched with the programmatic-stream-serialization attribute the next kernel's CTAs are scheduled while the
+// previous kernel drains, run their private prologue (shared-memory set-up, TMEM allocation) and block in pe_grid_dep_wait() until the
+// previous grid has completed and its memory is visible.  A kernel launched without the attribute sees both calls as no-ops.
+// PE_PDL=0 in the environment launches everything fully serialised.
+bool pe_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pe_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pe_grid_dep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pe_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pe_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // launchers (defined in the .cu files)
 int pe_launch_resid_simt(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st);

@@ -6,38 +6,54 @@
 
 namespace {
 
-#define RED_TX 32      // float4 columns per block
-#define RED_TY 16      // slot groups per block
+#define RED_TX 32      // peer-memory kernel: float4 columns per block (one arrival flag per block and peer: few, wide blocks)
+#define RED_TY 32      //                     slot groups per block -- the SAME count as RA_TY: the summation order over the slots depends on it
+                       //                     alone, and the peer path must stay bit-identical to reduce -> NCCL all-reduce -> Adam
+#define RA_TX 8        // single-GPU kernels: 8 float4 columns (one 128-byte line per slot) x 32 slot groups per block -> four times the blocks
+#define RA_TY 32       // (360 for the 5x50 net): the reduction is a latency chain of L2 loads, more CTAs in flight shorten it
 
-// blockDim = (RED_TX, RED_TY).  Thread (tx, ty) sums slots ty, ty+RED_TY, ... of float4 column i4 (4 loads in
-// flight), the RED_TY partials are then added in fixed order by ty == 0: deterministic for a given n_slots.
+// blockDim = (TX, TY).  Thread (tx, ty) sums slots ty, ty+TY, ... of float4 column i4 (4 loads in flight), the TY partials are
+// then added in a fixed order (groups of 8, then the group sums, by ty == 0): deterministic for a given n_slots.
+template <int TX, int TY>
 __device__ __forceinline__ float4 sum_slots4(const float* __restrict__ partials, int n_slots, int stride, int i4, bool in_range) {
-    __shared__ float4 red[RED_TY][RED_TX];
+    __shared__ float4 red[TY][TX];
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_range) {
         const float4* p = reinterpret_cast<const float4*>(partials) + i4;
         const size_t stride4 = (size_t)(stride >> 2);
         int k = threadIdx.y;
-        for (; k + 3 * RED_TY < n_slots; k += 4 * RED_TY) {
+        for (; k + 3 * TY < n_slots; k += 4 * TY) {
             float4 a = __ldcg(p + (size_t)(k) * stride4);
-            float4 b = __ldcg(p + (size_t)(k + RED_TY) * stride4);
-            float4 c = __ldcg(p + (size_t)(k + 2 * RED_TY) * stride4);
-            float4 d = __ldcg(p + (size_t)(k + 3 * RED_TY) * stride4);
+            float4 b = __ldcg(p + (size_t)(k + TY) * stride4);
+            float4 c = __ldcg(p + (size_t)(k + 2 * TY) * stride4);
+            float4 d = __ldcg(p + (size_t)(k + 3 * TY) * stride4);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
             s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
             s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
             s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
         }
-        for (; k < n_slots; k += RED_TY) {
+        for (; k < n_slots; k += TY) {
             float4 a = __ldcg(p + (size_t)k * stride4);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
     }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
+    constexpr int G = 8;                        // rows ty < TY / G each add the G partials ty * G .. ty * G + G - 1
+    if (threadIdx.y < TY / G) {
+        s = red[threadIdx.y * G][threadIdx.x];
+#pragma unroll
+        for (int r = 1; r < G; ++r) {
+            float4 a = red[threadIdx.y * G + r][threadIdx.x];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.y < TY / G) red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
     if (threadIdx.y == 0) {
 #pragma unroll
-        for (int r = 1; r < RED_TY; ++r) {
+        for (int r = 1; r < TY / G; ++r) {
             float4 a = red[r][threadIdx.x];
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
@@ -71,9 +87,9 @@ __device__ __forceinline__ void adam4(float4& p, float4 g, float4& m, float4& v,
 }
 
 __global__ void reduce_kernel(const float* __restrict__ gp, const float* __restrict__ tp, int n_slots, int total, float* __restrict__ out, float* __restrict__ tcopy) {
-    int i4 = blockIdx.x * RED_TX + threadIdx.x;
+    int i4 = blockIdx.x * RA_TX + threadIdx.x;
     const bool in_range = i4 < (total >> 2);
-    float4 s = sum_slots4(gp, n_slots, total, i4, in_range);
+    float4 s = sum_slots4<RA_TX, RA_TY>(gp, n_slots, total, i4, in_range);
     if (in_range && threadIdx.y == 0) reinterpret_cast<float4*>(out)[i4] = s;
     if (blockIdx.x == 0) reduce_terms(tp, n_slots, out + total, tcopy);
 }
@@ -106,11 +122,13 @@ __global__ void adam_kernel(float* __restrict__ params, const float* __restrict_
 __global__ void reduce_adam_kernel(const float* __restrict__ gp, const float* __restrict__ tp, int n_slots, int total, float* __restrict__ out, float* __restrict__ tcopy,
                                    float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
                                    int* __restrict__ d_step, unsigned int* __restrict__ ticket, float lr, float b1, float b2, float eps) {
+    pe_grid_dep_wait();          // gradient partials of the residual kernel(s)
+    pe_grid_dep_trigger();       // the next step's first kernel may be scheduled (it waits for this grid before it reads the parameters)
     const int step = *reinterpret_cast<volatile int*>(d_step) + 1;
     const float lr_t = adam_lr_t(step, lr, b1, b2);
-    int i4 = blockIdx.x * RED_TX + threadIdx.x;
+    int i4 = blockIdx.x * RA_TX + threadIdx.x;
     const bool in_range = i4 < (total >> 2);
-    float4 g = sum_slots4(gp, n_slots, total, i4, in_range);
+    float4 g = sum_slots4<RA_TX, RA_TY>(gp, n_slots, total, i4, in_range);
     if (in_range && threadIdx.y == 0) {
         reinterpret_cast<float4*>(out)[i4] = g;
         float4 p = reinterpret_cast<float4*>(params)[i4];
@@ -168,12 +186,14 @@ __global__ void reduce_peer_adam_kernel(const float* __restrict__ gp, const floa
                                         float* __restrict__ tcopy, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
                                         int* __restrict__ d_step, unsigned int* __restrict__ ticket, float lr, float b1, float b2, float eps,
                                         PeerArgs pa, unsigned int seq, int do_adam) {
+    pe_grid_dep_wait();
+    pe_grid_dep_trigger();
     int step = 0;
     float lr_t = 0.f;
     if (do_adam) { step = *reinterpret_cast<volatile int*>(d_step) + 1; lr_t = adam_lr_t(step, lr, b1, b2); }
     const int i4 = blockIdx.x * RED_TX + threadIdx.x;
     const bool in_range = i4 < (total >> 2);
-    const float4 s = sum_slots4(gp, n_slots, total, i4, in_range);
+    const float4 s = sum_slots4<RED_TX, RED_TY>(gp, n_slots, total, i4, in_range);
     const int buf = (int)(seq & 1u);
     const int lane = threadIdx.x;
     const size_t row = (size_t)pa.n;
@@ -236,8 +256,8 @@ extern "C" int pe_reduce_partials(const pe_plan* plan, const float* d_grad_parti
     if (!plan) { pe_set_error("null plan"); return 1; }
     int total = plan->lay.total;
     int n4 = total / 4;
-    int grid = (n4 + RED_TX - 1) / RED_TX;
-    dim3 bs(RED_TX, RED_TY);
+    int grid = (n4 + RA_TX - 1) / RA_TX;
+    dim3 bs(RA_TX, RA_TY);
     reduce_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("reduce_kernel: %s", cudaGetErrorString(e)); return 3; }
@@ -264,12 +284,11 @@ extern "C" int pe_reduce_adam(const pe_plan* plan, const float* d_grad_partials,
     if (!plan) { pe_set_error("null plan"); return 1; }
     int total = plan->lay.total;
     int n4 = total / 4;
-    int grid = (n4 + RED_TX - 1) / RED_TX;
-    dim3 bs(RED_TX, RED_TY);
-    reduce_adam_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
-                                                             d_params, d_m, d_v, d_step, reinterpret_cast<unsigned int*>(d_step + 1),
-                                                             lr, beta1, beta2, eps);
-    cudaError_t e = cudaGetLastError();
+    int grid = (n4 + RA_TX - 1) / RA_TX;
+    dim3 bs(RA_TX, RA_TY);
+    cudaError_t e = pe_launch_pdl(reduce_adam_kernel, dim3(grid), bs, 0, (cudaStream_t)stream, d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
+                                  d_params, d_m, d_v, d_step, reinterpret_cast<unsigned int*>(d_step + 1), lr, beta1, beta2, eps);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("reduce_adam_kernel: %s", cudaGetErrorString(e)); return 3; }
     return 0;
 }
@@ -368,10 +387,10 @@ extern "C" int pe_reduce_peer(const pe_plan* plan, pe_comm* c, const float* d_gr
     const int total = plan->lay.total;
     dim3 bs(RED_TX, RED_TY);
     const int do_adam = d_params != nullptr;
-    reduce_peer_adam_kernel<<<c->n_cta, bs, 0, (cudaStream_t)stream>>>(d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
-                                                                       d_params, d_m, d_v, d_step, do_adam ? reinterpret_cast<unsigned int*>(d_step + 1) : nullptr,
-                                                                       lr, beta1, beta2, eps, pa, c->seq, do_adam);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = pe_launch_pdl(reduce_peer_adam_kernel, dim3(c->n_cta), bs, 0, (cudaStream_t)stream, d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
+                                  d_params, d_m, d_v, d_step, do_adam ? reinterpret_cast<unsigned int*>(d_step + 1) : nullptr,
+                                  lr, beta1, beta2, eps, pa, c->seq, do_adam);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("reduce_peer_adam_kernel: %s", cudaGetErrorString(e)); return 3; }
     return 0;
 }

@@ -72,14 +72,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // Bounded: a phase that does not complete within ~2 s of SM clock (a tile takes ~100 us) is a protocol error -- trap (the launch
 // fails with an error the host reports) instead of spinning on the SM forever.  (A poll count is not a time bound: one try_wait may
 // suspend the thread for a hardware-defined interval; round 2 saw a 2^26-poll bound outlive a 300 s test timeout.)
+// The retries carry a suspend-time hint: without one a failed try_wait returns after a few cycles and the waiting warps poll -- ncu
+// counted half of the kernel's executed instructions in this loop, on the schedulers the epilogue warps need; with the hint the warp
+// sleeps in hardware until the phase completes (wake-up ~60 cycles) or the hint expires.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return;
     const long long t0 = clock64();
-    for (uint32_t spin = 1; !ok; ++spin) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if ((spin & 63u) == 0u && clock64() - t0 > (1ll << 32)) __trap();
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        if (!ok && clock64() - t0 > (1ll << 32)) __trap();
     }
 }
 // release-arrive of one thread (the generic-proxy writes before it were made visible to the async proxy by fence_async_smem)

@@ -41,13 +41,27 @@ using namespace pe_tcc;
 #ifndef TCF_EW
 #define TCF_EW 12
 #endif
-// TCF_ISSUERS = 2: a second issuing thread (lane 0 of the next control warp) drives the weight / bias gradient phase of the reverse sweep
-// -- bulk copies of the stash, its MMAs, the slot hand-shakes -- while the first one issues the adjoint MMAs: one thread's tcgen05.mma
-// issue costs ~64 cycles per instruction, two threads together reach ~40 (tests/probe_umma_timing.py).
-#ifndef TCF_ISSUERS
-#define TCF_ISSUERS 2
+// unroll factor of the forward epilogue loops over the 4-unit groups of a thread (A/B knob)
+#ifndef TCF_FWD_UNROLL
+#define TCF_FWD_UNROLL 1
 #endif
-static_assert(TCF_EW == 8 || TCF_EW == 12, "TCF_EW: 8 or 12 epilogue warps");
+#define TCF_PRAGMA_(x) _Pragma(#x)
+#define TCF_PRAGMA(x) TCF_PRAGMA_(x)
+// Two issuing threads: lane 0 of the second control warp drives the weight / bias gradient phases of the reverse sweep -- bulk copies of the
+// stash, its MMAs, the slot hand-shakes -- while lane 0 of the first one issues the adjoint MMAs: one thread's tcgen05.mma issue costs ~64
+// cycles per instruction, two threads together reach ~40 (tests/probe_umma_timing.py; same-box A/B against one issuer: -4.8 % per step).
+static_assert(TCF_EW == 8 || TCF_EW == 12 || TCF_EW == 16, "TCF_EW: 8, 12 or 16 epilogue warps");
+// register split of the 64 K registers (setmaxnreg, per warpgroup): control warpgroup / epilogue warps
+#if TCF_EW == 8
+#define TCF_REG_CTRL "104"
+#define TCF_REG_EPI "200"
+#elif TCF_EW == 12
+#define TCF_REG_CTRL "104"
+#define TCF_REG_EPI "136"
+#else      // 16 epilogue warps: 640 threads are launched with 96 registers; 64 / 112 needs the whole file and did not start on hardware
+#define TCF_REG_CTRL "64"
+#define TCF_REG_EPI "104"
+#endif
 constexpr int F_EPI = 32 * TCF_EW, F_THREADS = F_EPI + 128;
 constexpr int F_NH = TCF_EW / 4;                  // unit groups per TMEM lane quadrant
 constexpr int F_MAXG = (14 + F_NH - 1) / F_NH;    // 4-unit groups one epilogue thread owns at most (14 per 56-unit plane)
@@ -68,11 +82,13 @@ constexpr int F_COORD = F_MISC + 256;
 constexpr int F_RED = F_COORD + 128 * 16;
 constexpr int F_BIAS = F_RED + 4096;                          // [PE_MAX_LAYERS][64] floats
 constexpr int F_W0 = F_BIAS + PE_MAX_LAYERS * 256;            // [4][64] floats
-constexpr int F_TOTAL = F_W0 + 1024;                          // 229,632
+constexpr int F_XBLK = F_W0 + 1024;                           // [128 points][8 x fp16]: (x, y, t, 1) hi | (x, y, t, 0) lo of the tile: B operand of the layer-1 gradient MMAs
+constexpr int F_TOTAL = F_XBLK + 2048;                        // 231,680
 static_assert(2 * F_IMG <= F_IMG + 2 * F_STREAM, "the forward image double buffer lives inside the reverse-sweep region");
 static_assert(F_TOTAL <= 227 * 1024, "shared memory map exceeds the 227 KB opt-in limit");
-constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SDONE = 80, B_SFREE = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144, B_DRAINED = 160, B_REVGO = 168, B_REVDONE = 176;   // byte offsets in F_MISC
+constexpr int B_ACC = 0, B_ACT = 24, B_IMG = 48, B_SFULL = 64, B_SDONE = 80, B_SFREE = 96, B_DW = 128, B_TMEM = 136, B_SCALE = 144, B_DRAINED = 160, B_REVGO = 168, B_REVDONE = 176, B_L1 = 184;   // byte offsets in F_MISC
 constexpr uint32_t T_ACC = 0, T_DW = 320, T_BIAS = 432;       // tensor-memory columns (dW tile: 128 lanes x 112; bias tile: 128 lanes x 8)
+constexpr uint32_t T_L1 = 448;                                // layer-1 gradient: 4 tiles of 8 columns (value stream x [x y t 1 | lo parts], column sums of d/dx, d/dy, d/dt)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 template <int NS> __device__ __forceinline__ int grp_first(int g) { return g == 0 ? 0 : (g == 1 ? 1 : 3); }
@@ -170,6 +186,8 @@ __device__ __forceinline__ void act_bwd2(f2 (&ab)[K], const f2 (&A)[K]) {
 // Operand images per matrix m: forward B operand [n = out unit j][k = in unit i] at [(i >> 3)][j][i & 7] and adjoint B operand
 // [n = i][k = j] at [(j >> 3)][i][j & 7], each as an fp16 pair (hi image, then lo image), zero padded to 64 x 64.  16 blocks of 256 per matrix.
 __global__ void tcf_image_kernel(const float* __restrict__ params, PeLayout lay, uint8_t* __restrict__ images) {
+    pe_grid_dep_wait();          // the parameters come from the previous step's Adam kernel
+    pe_grid_dep_trigger();       // the residual kernel may start its prologue (it waits for this grid before it touches the images)
     const int m = blockIdx.x >> 4;
     const int din = lay.d[m], dout = lay.d[m + 1], ldw = lay.ldw[m];
     const float* W = params + lay.woff[m];
@@ -254,7 +272,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     const pe_term_desc& T2 = args.term2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = lay.L;
-    const bool prof_on = PROF && args.prof != nullptr && (int)blockIdx.x == args.prof_cta && (tid == 0 || tid == F_EPI || (TCF_ISSUERS == 2 && tid == F_EPI + 32));
+    const bool prof_on = PROF && args.prof != nullptr && (int)blockIdx.x == args.prof_cta && (tid == 0 || tid == F_EPI || tid == F_EPI + 32);
     long long prof_t = 0;
     (void)prof_on; (void)prof_t;
     uint8_t* act = smem + F_ACT;
@@ -268,9 +286,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     const uint32_t bar0 = smem_u32(smem + F_MISC);
     const uint32_t bar_acc = bar0 + B_ACC, bar_act = bar0 + B_ACT, bar_img = bar0 + B_IMG;
     const uint32_t bar_sfull = bar0 + B_SFULL, bar_sdone = bar0 + B_SDONE, bar_sfree = bar0 + B_SFREE, bar_dw = bar0 + B_DW, bar_drained = bar0 + B_DRAINED;
-    const uint32_t bar_revgo = bar0 + B_REVGO, bar_revdone = bar0 + B_REVDONE;
+    const uint32_t bar_revgo = bar0 + B_REVGO, bar_revdone = bar0 + B_REVDONE, bar_l1 = bar0 + B_L1;
 
+    pe_grid_dep_trigger();                           // the reduction kernel's CTAs may be scheduled as SMs drain (they wait for this grid)
     for (int i = tid; i < F_TOTAL / 16; i += F_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pe_grid_dep_wait();                              // operand images (previous kernel) and, through it, the parameters of the last Adam step
     const int slot = A.slot_base + blockIdx.x;
     float* gpart = A.grad_partials + (size_t)slot * lay.total;
     uint8_t* stash = reinterpret_cast<uint8_t*>(A.stash + (size_t)blockIdx.x * A.stash_floats);
@@ -295,7 +315,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
         for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sdone + 8 * b, 1); mbar_init(bar_sfree + 8 * b, F_EPI); }
         mbar_init(bar_dw, 1);
         mbar_init(bar_drained, F_EPI);
-        mbar_init(bar_revgo, 1); mbar_init(bar_revdone, 1);
+        mbar_init(bar_revgo, 1); mbar_init(bar_revdone, 1); mbar_init(bar_l1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == F_CTRL) {
@@ -315,13 +335,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
 
     if (warp >= F_CTRL) {
         // ============================================================================================ control warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " TCF_REG_CTRL ";");
         if (warp == F_CTRL && lane == 0) {
             uint32_t pact = 0, pimg = 0, psfull = 0, psfree = 0;      // parity bits of the phases this thread waits for next
-            uint32_t pdrained = 1;                                    // ... of the PREVIOUS drain: the first wait passes on the fresh barrier
             uint32_t prevdone = 0;
-            (void)pdrained; (void)prevdone; (void)psfull; (void)psfree;
-            uint32_t n_acc2 = 0, n_dw = 0;
+            (void)psfull; (void)psfree;
+            uint32_t n_acc2 = 0;
             const bool fast = args.fast != 0;
             auto load_fwd = [&](int i) {
                 const uint32_t b = (uint32_t)(i & 1);
@@ -378,128 +397,49 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
                 mbar_expect_tx(bar_img, F_IMG);
                 tma_load_1d(r_s, adj_src(L), F_IMG, bar_img);
-#if TCF_ISSUERS == 2
                 mbar_arrive(bar_revgo);                      // the second issuer may start this tile's gradient phases (the staging slots are free)
                 for (int l = L; l >= 2; --l) {
                     const int dout = lay.d[l];
                     wait_img(0);
                     TCF_PROF(24);
-                    wait_act(0); wait_act(1); wait_act(2);
-                    TCF_PROF(25);
-                    fence_after();
-                    if (sec) issue_group<0, 1>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
-                    else issue_group<0, NS>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
-                    mma_commit(bar_acc);
-                    mma_commit(bar_acc + 8);
-                    mma_commit(bar_acc + 16);
+                    // every jet stream is its own product abar_k = Zbar_k W^T and the epilogue warps take the streams one at a time (d/dx first, the
+                    // value stream last): group by group in that order, one commit each.  They publish Zbar_{l,1..2} (G1) as soon as those two
+                    // planes are written, two passes before the rest: the 24 MMAs of G1 run under those passes (same-box A/B of the group order
+                    // alone: -0.45 % per step; profiles/r2_ab_shot21.txt)
+                    {
+                        const int ks = (dout + 15) >> 4;
+                        const uint32_t id = idesc_km(64);
+                        wait_act(1);
+                        TCF_PROF(25);
+                        fence_after();
+                        if (!sec) issue_group<1, 2>(tbase, a_lo, b_lo0, km_hi, id, ks);
+                        mma_commit(bar_acc + 8);
+                        wait_act(2);
+                        fence_after();
+                        if (!sec) issue_group<3, NS - 3>(tbase, a_lo, b_lo0, km_hi, id, ks);
+                        mma_commit(bar_acc + 16);
+                        wait_act(0);
+                        fence_after();
+                        issue_group<0, 1>(tbase, a_lo, b_lo0, km_hi, id, ks);
+                        mma_commit(bar_acc);
+                    }
                     ++n_acc2;
                     TCF_PROF(26);
-                    if (l > 2) {                             // the adjoint image is free once this layer's adjoint MMAs are complete
-                        mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
+                    if (l > 2) {                             // the adjoint image is free once this layer's adjoint MMAs are complete (G0 is the last group)
+                        mbar_wait(bar_acc, (n_acc2 - 1) & 1u);
                         mbar_expect_tx(bar_img, F_IMG);
                         tma_load_1d(r_s, adj_src(l - 1), F_IMG, bar_img);
                     }
                 }
                 mbar_wait(bar_revdone, prevdone);            // every gradient MMA of the tile is complete and both staging slots are free
                 prevdone ^= 1u;
+                pact ^= 7u;                                  // the Zbar_1 publish (layer-1 gradient MMAs) is the second issuer's phase; it is complete by now
                 if (tile + (int)gridDim.x < ntiles) {
                     load_fwd(2);
                     if (L >= 3) load_fwd(3);
                 }
-#else
-                for (int l = L; l >= 2; --l) {
-                    const int dout = lay.d[l];
-                    const uint8_t* stash_in = stash + (size_t)(l - 2) * STASH_LAYER;     // outputs of layer l-1 = inputs A of layer l
-                    // the stashed planes of A_{l-1} come back one stream (hi plane | lo plane, 28,672 B) per bulk copy into two staging slots
-                    auto load_stage = [&](int k) {
-                        const uint32_t sb = (uint32_t)(k & 1);
-                        mbar_expect_tx(bar_sfull + 8 * sb, F_STREAM);
-                        tma_load_1d(stg_s + sb * F_STREAM, stash_in + (size_t)k * F_STREAM, F_STREAM, bar_sfull + 8 * sb);
-                    };
-                    const int nst = sec ? 1 : NS;               // streams of this tile
-                    load_stage(0);                              // both slots are free: the previous layer's DW phase is complete
-                    if (!sec) load_stage(1);
-                    if (l > 2) {                                // pull the planes of the next (shallower) layer towards L2 while this layer runs
-                        const uint8_t* nxt = stash + (size_t)(l - 3) * STASH_LAYER;
-#pragma unroll
-                        for (int k = 0; k < NS; ++k)
-                            if (k < nst) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + (size_t)k * F_STREAM), "r"(F_STREAM) : "memory");
-                    }
-                    wait_img(0);
-                    TCF_PROF(24);
-                    wait_act(0); wait_act(1); wait_act(2);
-                    TCF_PROF(25);
-                    fence_after();
-                    if (sec) issue_group<0, 1>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
-                    else issue_group<0, NS>(tbase, a_lo, b_lo0, km_hi, idesc_km(64), (dout + 15) >> 4);
-                    mma_commit(bar_acc);
-                    mma_commit(bar_acc + 8);
-                    mma_commit(bar_acc + 16);
-                    ++n_acc2;
-                    TCF_PROF(26);
-                    // ---- weight gradient  dW = sum_k A_k^T Zbar_k  (K = 128 points, 8 K-steps of 16) as ONE M = 128 MMA per K-step: the A operand is
-                    //      the staged stream read MN-major, rows 0..55 = Ah units, rows 56..111 = Al units (rows 112..127: whatever follows the slot,
-                    //      ignored); the B operand [Zh | Zl] (N = 112).  Tile: rows i, columns j: Ah^T Zh | rows i, columns 56 + j: Ah^T Zl | rows 56 + i,
-                    //      columns j: Al^T Zh (the cross products carry 2^11 and are resolved when the tile is drained).  The MMA count, not the MMA
-                    //      size, is what the tensor pipe charges for at these shapes (tests/probe_umma_timing.py: ~64 cycles per instruction up to N = 128).
-                    // the gradient tiles of the previous layer (or tile) must have been drained before they are overwritten; the epilogue warps
-                    // publish Zbar first and drain afterwards, behind the adjoint MMAs issued above
-                    mbar_wait(bar_drained, pdrained);
-                    pdrained ^= 1u;
-                    const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
-                    const uint32_t id112 = idesc_mn(112), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
-#pragma unroll 1
-                    for (int k = 0; k < nst; ++k) {
-                        const uint32_t sb = (uint32_t)(k & 1);
-                        mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
-                        psfull ^= 1u << sb;
-                        const uint32_t ga = g_lo + sb * (uint32_t)(F_STREAM >> 4);
-                        const uint32_t zh = z_lo + (uint32_t)k * (uint32_t)(F_STREAM >> 4), zl = zh + (uint32_t)(F_PLANE >> 4);
-#pragma unroll
-                        for (int s = 0; s < 8; ++s) {                        // K-steps of 16 points = 256 B
-                            const uint64_t da = mk_desc(ga + 16u * s, mn_hi);
-                            const uint32_t first = (k > 0 || s > 0) ? 1u : 0u;
-                            if (nzc == 7) {                                  // the two Z planes are contiguous: one N = 112 MMA
-                                mma_bf16_ss(tbase + T_DW, da, mk_desc(zh + 16u * s, mn_hi), id112, first);
-                            } else {
-                                mma_bf16_ss(tbase + T_DW, da, mk_desc(zh + 16u * s, mn_hi), idz, first);
-                                mma_bf16_ss(tbase + T_DW + 56, da, mk_desc(zl + 16u * s, mn_hi), idz, first);
-                            }
-                        }
-                        if (k == 0) {
-                            // bias gradient: column 0 of  [Zh | Zl]^T 1: the value-stream planes as MN-major A operand (M = 128: rows 0..55 sums
-                            // of Zh, rows 56..111 sums of Zl), a block of ones as B operand (N = 8)
-#pragma unroll
-                            for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_BIAS, mk_desc(z_lo + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
-                        }
-                        mma_commit(bar_sdone + 8 * sb);        // the epilogue warps' pass over stream k starts (staged planes + accumulators -> Zbar_{l-1,k})
-                        if (k >= 1 && k + 1 < nst) {           // slot of stream k - 1: refilled (stream k + 1) once the epilogue warps have read it
-                            const uint32_t ob = sb ^ 1u;
-                            mbar_wait(bar_sfree + 8 * ob, (psfree >> ob) & 1u);
-                            psfree ^= 1u << ob;
-                            load_stage(k + 1);
-                        }
-                    }
-                    mma_commit(bar_dw);
-                    ++n_dw;
-                    TCF_PROF(27);
-                    mbar_wait(bar_dw, (n_dw - 1) & 1u);      // every MMA of the layer is complete: the adjoint image is free
-                    mbar_wait(bar_sfree, psfree & 1u);       // ... and so are both staging slots once the last passes of the epilogue warps are through
-                    psfree ^= 1u;
-                    if (!sec) { mbar_wait(bar_sfree + 8, (psfree >> 1) & 1u); psfree ^= 2u; }
-                    TCF_PROF(28);
-                    if (l > 2) {
-                        mbar_expect_tx(bar_img, F_IMG);
-                        tma_load_1d(r_s, adj_src(l - 1), F_IMG, bar_img);
-                    } else if (tile + (int)gridDim.x < ntiles) {
-                        load_fwd(2);
-                        if (L >= 3) load_fwd(3);
-                    }
-                }
-#endif
             }
         }
-#if TCF_ISSUERS == 2
         else if (warp == F_CTRL + 1 && lane == 0) {
             // ---------------------------------------------------------------- second issuer: weight / bias gradient phases of the reverse sweep
             uint32_t pact = 0, psfull = 0, psfree = 0, pdrained = 1, prevgo = 0, n_dw = 0;
@@ -563,9 +503,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                                 mma_bf16_ss(tbase + T_DW + 56, da, mk_desc(zl + 16u * s, mn_hi), idz, first);
                             }
                         }
-                        if (k == 0) {
+                        if (k == nst - 1) {
                             // bias gradient: column 0 of  [Zh | Zl]^T 1: the value-stream planes as MN-major A operand (M = 128: rows 0..55 sums
-                            // of Zh, rows 56..111 sums of Zl), a block of ones as B operand (N = 8)
+                            // of Zh, rows 56..111 sums of Zl), a block of ones as B operand (N = 8).  With the LAST stream (whose completion the pass
+                            // that overwrites the value-stream plane waits for): the first passes of the epilogue warps start 8 MMAs earlier
 #pragma unroll
                             for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_BIAS, mk_desc(z_lo + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
                         }
@@ -586,22 +527,38 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     if (!sec) { mbar_wait(bar_sfree + 8, (psfree >> 1) & 1u); psfree ^= 2u; }
                     TCF_PROF(28);
                 }
-                mbar_arrive(bar_revdone);
+                // ---- layer-1 gradient  dW_0 = sum_k X_k^T Zbar_1,k, db_0 = Zbar_1,0^T 1  on the tensor pipe: the input jets are X_0 = (x, y, t) and constant
+                // unit vectors times the input scale for d/dx, d/dy, d/dt (zero for d2/dt2), so the products are  [Zh | Zl]^T [xh yh th 1 xl yl tl 0]
+                // (value stream; the B operand is the tile's coordinate block, one 16-byte row per point) and the column sums of the three first-
+                // derivative streams ([Zh | Zl]^T 1, the ones block).  The epilogue warps spent 7 % of a tile on these sums in scalar code.
+                wait_act(0); wait_act(1); wait_act(2);
+                fence_after();
+                {
+                    const uint32_t id8 = idesc_mn(8);
+                    const uint32_t x_lo = desc_lo(smem_u32(smem + F_XBLK), 128);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + T_L1, mk_desc(z_lo + 16u * s, mn_hi), mk_desc(x_lo + 16u * s, desc_hi(256)), id8, s > 0 ? 1u : 0u);
+                    if (!sec) {
+#pragma unroll
+                        for (int k = 1; k < 4; ++k)
+#pragma unroll
+                            for (int s = 0; s < 8; ++s)
+                                mma_bf16_ss(tbase + T_L1 + 8u * k, mk_desc(z_lo + (uint32_t)k * (uint32_t)(F_STREAM >> 4) + 16u * s, mn_hi), d_ones, id8, s > 0 ? 1u : 0u);
+                    }
+                    mma_commit(bar_l1);
+                }
+                TCF_PROF(29);
+                mbar_arrive(bar_revdone);                    // (after the wait above: the first issuer skips that ACT phase and must find it complete)
             }
         }
-#endif
         __syncwarp();
     } else {
         // ============================================================================================ epilogue warps
-#if TCF_EW == 8
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-#else
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
-#endif
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " TCF_REG_EPI ";");
         const int p = 32 * (warp & 3) + lane;            // TMEM lane = point of the tile
         const int h = warp >> 2;                         // unit group: 4-unit groups [n4 h / F_NH, n4 (h + 1) / F_NH) of a layer with n4 groups
         const uint32_t tlane = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
-        uint32_t pacc = 0, pdw = 0, psdone = 0;
+        uint32_t pacc = 0, pdw = 0, psdone = 0, pl1 = 0;
         auto wait_acc = [&](int g) { mbar_wait(bar_acc + 8 * g, (pacc >> g) & 1u); pacc ^= 1u << g; };
         auto publish = [&](int g) { mbar_arrive(bar_act + 8 * g); };
         // planes in shared memory were written through the generic proxy and are read next by MMAs (async proxy): a shared-memory proxy fence
@@ -643,8 +600,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
             if (h == 0) {
                 float x = 0.f, y = 0.f, t = 0.f;
                 if (valid) { x = row[0]; y = row[1]; t = row[2]; }
-                *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(fmaf(x, Tc.in_scale[0], Tc.in_shift[0]), fmaf(y, Tc.in_scale[1], Tc.in_shift[1]),
-                                                                        fmaf(t, Tc.in_scale[2], Tc.in_shift[2]), valid ? 1.f : 0.f);
+                const float xn = fmaf(x, Tc.in_scale[0], Tc.in_shift[0]), yn = fmaf(y, Tc.in_scale[1], Tc.in_shift[1]), tn = fmaf(t, Tc.in_scale[2], Tc.in_shift[2]);
+                *reinterpret_cast<float4*>(coord + 4 * p) = make_float4(xn, yn, tn, valid ? 1.f : 0.f);
+                uint32_t h01, l01, h23, l23;                 // coordinate block row of this point: xh yh th 1 | xl yl tl 0  (fp16 pairs)
+                split2(F2(xn, yn), h01, l01);
+                split2(F2(tn, 1.f), h23, l23);
+                *reinterpret_cast<uint4*>(smem + F_XBLK + 16 * p) = make_uint4(h01, h23, l01, l23);
             } else if (h == 1) {
                 const int nt = tile + (int)gridDim.x;                      // pull this CTA's next tile towards L2
                 if (nt < ntiles) {
@@ -665,24 +626,32 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
             {
                 const float4 c4v = *reinterpret_cast<const float4*>(coord + 4 * p);
                 const int d1 = lay.d[1];
+                // two units per instruction (packed fp32 pairs), the algebra of the hidden-layer epilogues: a = tanh(z + b), s = 1 - a^2,
+                // a_k = s z_k, a_tt = s z_tt - 2 a a_t z_t with z_x = sx w0, z_y = sy w1, z_t = st w2, z_tt = 0 (the input is linear in x, y, t)
+                const f2 cx = F2(c4v.x), cy = F2(c4v.y), ct = F2(c4v.z);
+                const f2 sx = F2(Tc.in_scale[0]), sy = F2(Tc.in_scale[1]), stt = F2(Tc.in_scale[2]);
 #pragma unroll 1
                 for (int c4 = c4_lo(d1); c4 < c4_hi(d1); ++c4) {
-                    float o[NS][4];
+                    f2 o[NS][2];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = 4 * c4 + u;                           // pads: zero weights and bias -> tanh(0) = 0, zero derivatives
-                        float z[NS];
-                        const float w0 = sw0[j], w1 = sw0[64 + j], w2 = sw0[128 + j];
-                        z[0] = fmaf(c4v.x, w0, fmaf(c4v.y, w1, c4v.z * w2));
-                        z[1] = Tc.in_scale[0] * w0; z[2] = Tc.in_scale[1] * w1; z[3] = Tc.in_scale[2] * w2;
-                        if (NS == 5) z[NS - 1] = 0.f;
-                        act_fwd<NS, true>(z, sw0[192 + j]);
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) o[k][u] = z[k];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int j = 4 * c4 + 2 * hh;                      // pads: zero weights and bias -> tanh(0) = 0, zero derivatives
+                        const f2 w0 = *reinterpret_cast<const f2*>(sw0 + j), w1 = *reinterpret_cast<const f2*>(sw0 + 64 + j);
+                        const f2 w2 = *reinterpret_cast<const f2*>(sw0 + 128 + j), bb = *reinterpret_cast<const f2*>(sw0 + 192 + j);
+                        const f2 z = __ffma2_rn(cx, w0, __ffma2_rn(cy, w1, __ffma2_rn(ct, w2, bb)));
+                        const f2 a = tanh2(z);
+                        const f2 sd = F2(fmaf(-a.x, a.x, 1.f), fmaf(-a.y, a.y, 1.f));
+                        const f2 zt = __fmul2_rn(stt, w2);
+                        const f2 at = __fmul2_rn(sd, zt);
+                        o[0][hh] = a;
+                        o[1][hh] = __fmul2_rn(sd, __fmul2_rn(sx, w0));
+                        o[2][hh] = __fmul2_rn(sd, __fmul2_rn(sy, w1));
+                        o[3][hh] = at;
+                        if (NS == 5) o[NS - 1][hh] = __fmul2_rn(__fmul2_rn(__fmul2_rn(a, at), zt), F2(-2.f));
                     }
 #pragma unroll
                     for (int k = 0; k < NS; ++k)
-                        if (k == 0 || !sec) put4(stash, k, c4, F2(o[k][0], o[k][1]), F2(o[k][2], o[k][3]));      // stash layer 0 = outputs of layer 1
+                        if (k == 0 || !sec) put4(stash, k, c4, o[k][0], o[k][1]);      // stash layer 0 = outputs of layer 1
                 }
                 publish_fences();
                 publish(0); publish(1); publish(2);
@@ -697,7 +666,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 wait_acc(0);
                 TCF_PROF(1);
                 fence_after();
-#pragma unroll 1
+TCF_PRAGMA(unroll TCF_FWD_UNROLL)
                 for (int c4 = lo4; c4 < hi4; ++c4) {
                     float z[4];
                     tm_ld4(tlane + T_ACC + 4 * c4, z);
@@ -712,7 +681,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 wait_acc(1);
                 TCF_PROF(3);
                 fence_after();
-#pragma unroll 1
+TCF_PRAGMA(unroll TCF_FWD_UNROLL)
                 for (int c4 = lo4; c4 < (sec ? lo4 : hi4); ++c4) {
                     float z1[4], z2[4];
                     f2 a01, a23;
@@ -731,7 +700,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 wait_acc(2);
                 TCF_PROF(5);
                 fence_after();
-#pragma unroll 1
+TCF_PRAGMA(unroll TCF_FWD_UNROLL)
                 for (int c4 = lo4; c4 < (sec ? lo4 : hi4); ++c4) {
                     float z3[4], z4[4];
                     f2 a01, a23;
@@ -822,9 +791,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 const int m = l - 1;
                 const int din = lay.d[l - 1], dout = lay.d[l];
                 const int lo4 = c4_lo(din), hi4 = c4_hi(din);
-                wait_acc(0); wait_acc(1); wait_acc(2);       // adjoint MMAs done: abar^{l-1} in the accumulators
-                TCF_PROF(9);
-                fence_after();
+                // (the wait for the adjoint MMAs -- abar^{l-1} in the accumulators -- sits inside the passes, behind the slot reads of streams 0 and 1
+                // that do not need them: the staging slots are handed back, and the bulk copies of streams 2 and 3 start, while those MMAs still run)
                 // ---- through tanh of layer l-1, one jet stream at a time, while the weight-gradient phase runs: as soon as the MMAs of stream k are
                 // complete (SDONE) this thread reads its entries of A_{l-1,k} from the staging slot the bulk copy filled -- the stash is read from
                 // L2 once, by the copy -- takes abar_k from tensor memory and overwrites the Zbar_l,k plane (no MMA reads it any more) with
@@ -836,6 +804,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     if (sec) {                       // primal-only tile: one stream, zbar_0 = s abar_0
                         mbar_wait(bar_sdone, psdone & 1u);
                         psdone ^= 1u;
+                        wait_acc(0); wait_acc(1); wait_acc(2);
+                        TCF_PROF(9);
+                        fence_after();
                         const uint8_t* slot = smem + F_STG;
 #pragma unroll 1
                         for (int c4 = lo4; c4 < hi4; ++c4) {
@@ -875,6 +846,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                             }
                             if (!(NS == 5 && k == 3)) mbar_arrive(bar_sfree + 8 * sb);     // stream 3's slot is read again by the last pass
                         }
+                        // adjoint MMAs of this stream's group done: abar_k^{l-1} in the accumulators (the issuer commits G1, G2, G0 in this order)
+                        if (k == 1) { wait_acc(1); TCF_PROF(9); fence_after(); }
+                        if (k == 3) { wait_acc(2); fence_after(); }
+                        if (k == NS - 1) { wait_acc(0); fence_after(); }
 #pragma unroll
                         for (int g = 0; g < F_MAXG; ++g) {
                             const int c4 = lo4 + g;
@@ -918,6 +893,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                             if (NS == 5) { mbar_arrive(bar_sfree); mbar_arrive(bar_sfree + 8); }
                             else mbar_arrive(bar_sfree + 8 * sb);
                         }
+                        // Zbar_{l-1,1..2} written: the next adjoint GEMM's first group may start under the last two passes (five streams only: with four
+                        // there is one pass left and the early MMAs just compete with the weight-gradient MMAs -- same-box A/B: K = 5 -0.75 %, K = 4 +1 %)
+                        if (NS == 5 && k == 2) { publish_fences(); publish(1); }
                         // the stashed planes of stream k have been copied to shared memory and nobody reads them again: drop their (dirty) L2 lines
                         // instead of letting them be written back to HBM -- the stash is scratch that the next tile overwrites.  Without this the
                         // whole stash (5.6 KB per point) goes to DRAM and the live part no longer fits L2 (ncu: 286 MB written per 55 k points).
@@ -929,10 +907,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     }
                 }
                 TCF_PROF(10);
-                if (l > 2) {                                 // Zbar_{l-1} is complete: the next layer's adjoint MMAs may start while the tiles are drained
-                    publish_fences();
-                    publish(0); publish(1); publish(2);
-                }
+                // Zbar_{l-1} is complete: the next layer's adjoint MMAs (l > 2) / the layer-1 gradient MMAs (l = 2) may start while the tiles are drained
+                // (five streams: G1 was published behind pass 2 unless this is a primal-only tile)
+                publish_fences();
+                publish(0); if (sec || NS != 5) publish(1); publish(2);
                 mbar_wait(bar_dw, pdw);                      // every weight / bias gradient MMA of the layer is complete
                 pdw ^= 1u;
                 TCF_PROF(11);
@@ -995,47 +973,45 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 mbar_arrive(bar_drained);                    // the issuer may overwrite the gradient tiles
                 TCF_PROF(12);
             }
-            // ================================================================ layer 1 gradient (3 x d1 + bias): FFMA, fixed-order reduce
-            named_bar_sync(1, F_EPI);
+            // ================================================================ layer 1 gradient (3 x d1 + bias): drain of the four 8-column tiles
+            // Rows r < d1: sums with Zh of unit r; rows 56 <= r < 56 + d1: sums with Zl of unit r - 56 (carry 2^11).  Tile 0 columns: Z^T xh, Z^T yh,
+            // Z^T th, Z^T 1, Z^T xl, Z^T yl, Z^T tl (carry 2^11), -; tiles 1..3: column 0 = column sums of the d/dx, d/dy, d/dt streams.  Two passes
+            // (hi rows, then lo rows) with a barrier in between: every element is updated in a fixed order.
+            mbar_wait(bar_l1, pl1);
+            pl1 ^= 1u;
+            fence_after();
             {
                 const int d1 = lay.d[1];
-                const int j = tid & 63, qq = tid >> 6;                    // 4 point quarters x 64 units
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gb = 0.f;
-                if (j < d1 && tid < 256) {
-                    const uint8_t* base = act + (j >> 3) * F_CH + (j & 7) * 2;
-#pragma unroll 4
-                    for (int s = 0; s < 32; ++s) {
-                        const int pp = 32 * qq + s;
-                        const float4 c4v = *reinterpret_cast<const float4*>(coord + 4 * pp);
-                        auto val = [&](int k) {
-                            const uint8_t* q = base + k * F_STREAM + pp * 16;
-                            return fmaf(__half2float(*reinterpret_cast<const __half*>(q + F_PLANE)), LO_INV, __half2float(*reinterpret_cast<const __half*>(q)));
-                        };
-                        const float zv = val(0), zx = sec ? 0.f : val(1), zy = sec ? 0.f : val(2), zt = sec ? 0.f : val(3);
-                        g0 = fmaf(c4v.x, zv, fmaf(Tc.in_scale[0], zx, g0));
-                        g1 = fmaf(c4v.y, zv, fmaf(Tc.in_scale[1], zy, g1));
-                        g2 = fmaf(c4v.z, zv, fmaf(Tc.in_scale[2], zt, g2));
-                        gb += zv;
+                const int r0 = 32 * (warp & 3), r = r0 + lane;
+                float* gW = gpart + lay.woff[0];
+                float* gB = gpart + lay.boff[0];
+                const int ldw = lay.ldw[0];
+                float gx = 0.f, gy = 0.f, gt = 0.f, gb = 0.f;
+                if (h == 0) {
+                    float v0[8], v1[8], v2[8], v3[8];
+                    tm_ld8(tlane + T_L1, v0);
+                    if (!sec) { tm_ld8(tlane + T_L1 + 8, v1); tm_ld8(tlane + T_L1 + 16, v2); tm_ld8(tlane + T_L1 + 24, v3); }
+                    tm_wait_ld();
+                    gx = fmaf(v0[4], LO_INV, v0[0]); gy = fmaf(v0[5], LO_INV, v0[1]); gt = fmaf(v0[6], LO_INV, v0[2]); gb = v0[3];
+                    if (!sec) { gx = fmaf(Tc.in_scale[0], v1[0], gx); gy = fmaf(Tc.in_scale[1], v2[0], gy); gt = fmaf(Tc.in_scale[2], v3[0], gt); }
+                    if (r < d1) {
+                        __stcg(gW + r, __ldcg(gW + r) + gx * inv_sigma);
+                        __stcg(gW + ldw + r, __ldcg(gW + ldw + r) + gy * inv_sigma);
+                        __stcg(gW + 2 * ldw + r, __ldcg(gW + 2 * ldw + r) + gt * inv_sigma);
+                        __stcg(gB + r, __ldcg(gB + r) + gb * inv_sigma);
                     }
                 }
-                if (tid < 256) *reinterpret_cast<float4*>(red + (qq * 64 + j) * 4) = make_float4(g0 * inv_sigma, g1 * inv_sigma, g2 * inv_sigma, gb * inv_sigma);
+                fence_before();
                 named_bar_sync(1, F_EPI);
-                if (tid < 64 && tid < d1) {
-                    float4 s = *reinterpret_cast<float4*>(red + tid * 4);
-#pragma unroll
-                    for (int r = 1; r < 4; ++r) {
-                        const float4 v = *reinterpret_cast<float4*>(red + (r * 64 + tid) * 4);
-                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                    }
-                    float* gW = gpart + lay.woff[0];
-                    const int ldw = lay.ldw[0];
-                    __stcg(gW + tid, __ldcg(gW + tid) + s.x);
-                    __stcg(gW + ldw + tid, __ldcg(gW + ldw + tid) + s.y);
-                    __stcg(gW + 2 * ldw + tid, __ldcg(gW + 2 * ldw + tid) + s.z);
-                    float* gB = gpart + lay.boff[0];
-                    __stcg(gB + tid, __ldcg(gB + tid) + s.w);
+                if (h == 0 && r >= 56 && r < 56 + d1) {
+                    const int j = r - 56;
+                    const float sc = LO_INV * inv_sigma;
+                    __stcg(gW + j, __ldcg(gW + j) + gx * sc);
+                    __stcg(gW + ldw + j, __ldcg(gW + ldw + j) + gy * sc);
+                    __stcg(gW + 2 * ldw + j, __ldcg(gW + 2 * ldw + j) + gt * sc);
+                    __stcg(gB + j, __ldcg(gB + j) + gb * sc);
                 }
-                named_bar_sync(1, F_EPI);
+                // (the next update of these elements is a tile away, behind the barrier at the start of the next tile)
             }
             TCF_PROF(13);
         }
@@ -1076,8 +1052,8 @@ int launch_tcf(const TcfArgs& t, int slots, cudaStream_t st) {
     auto kern = resid_tcf_kernel<NS, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F_TOTAL);
     if (e != cudaSuccess) { pe_set_error("cudaFuncSetAttribute(resid_tcf, %d): %s", F_TOTAL, cudaGetErrorString(e)); return 2; }
-    kern<<<slots, F_THREADS, F_TOTAL, st>>>(t);
-    e = cudaGetLastError();
+    e = pe_launch_pdl(kern, dim3(slots), dim3(F_THREADS), F_TOTAL, st, t);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("launch resid_tcf<%d>: %s", NS, cudaGetErrorString(e)); return 3; }
     return 0;
 }
@@ -1108,8 +1084,8 @@ int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int fa
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
     uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
     t.images = images;
-    tcf_image_kernel<<<plan->lay.L * 16, 256, 0, st>>>(a.params, a.lay, images);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = pe_launch_pdl(tcf_image_kernel, dim3(plan->lay.L * 16), dim3(256), 0, st, a.params, a.lay, images);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { pe_set_error("tcf_image_kernel: %s", cudaGetErrorString(e)); return 3; }
     if (K == 5) return g_tcf_prof ? launch_tcf<5, true>(t, slots, st) : launch_tcf<5, false>(t, slots, st);
     if (K == 4) return g_tcf_prof ? launch_tcf<4, true>(t, slots, st) : launch_tcf<4, false>(t, slots, st);

@@ -119,7 +119,7 @@ TCF_NAMES = ['E: tile start + layer1 fwd', 'E: fwd wait ACC[G0]', 'E: fwd epilog
              'E: fwd epilogue G2 (t,tt)', 'E: output layer wait', 'E: output/residual stage', 'E: rev wait adjoint MMAs', 'E: rev stream passes (waits + work)',
              'E: rev wait dW MMAs', 'E: dW drain + publish', 'E: layer1 grad', '-', '-',
              'I: fwd wait image', 'I: fwd wait ACT[G0]', 'I: fwd issue G0', 'I: fwd wait ACT[G1]', 'I: fwd issue G1', 'I: fwd wait ACT[G2]', 'I: fwd issue G2',
-             'I: fwd wait prev layer + TMA', 'I: rev wait image', 'I: rev wait ACT', 'I: adjoint issue', 'I: dW loop (waits + issue)', 'I: wait dW done + slots free', '-', '-', '-']
+             'I: fwd wait prev layer + TMA', 'I: rev wait image', 'I: rev wait ACT', 'I: adjoint issue', 'I: dW loop (waits + issue)', 'I: wait dW done + slots free', 'I: layer-1 gradient (wait + MMAs)', '-', '-']
 
 
 def prof(flush):
