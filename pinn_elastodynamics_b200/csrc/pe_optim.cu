@@ -191,20 +191,23 @@ __global__ void reduce_peer_adam_kernel(const float* __restrict__ gp, const floa
     int step = 0;
     float lr_t = 0.f;
     if (do_adam) { step = *reinterpret_cast<volatile int*>(d_step) + 1; lr_t = adam_lr_t(step, lr, b1, b2); }
-    const int i4 = blockIdx.x * RED_TX + threadIdx.x;
-    const bool in_range = i4 < (total >> 2);
-    const float4 s = sum_slots4<RED_TX, RED_TY>(gp, n_slots, total, i4, in_range);
     const int buf = (int)(seq & 1u);
     const int lane = threadIdx.x;
     const size_t row = (size_t)pa.n;
+    // the grid is capped at the number of SMs (every block of every rank is resident, so waiting for a peer's slice cannot starve the block
+    // that produces it); a block walks over its 128-float slices sl = blockIdx.x, + gridDim.x, ..., one arrival flag per slice and peer
+    for (int sl = blockIdx.x; sl < pa.n_cta; sl += gridDim.x) {
+    const int i4 = sl * RED_TX + threadIdx.x;
+    const bool in_range = i4 < (total >> 2);
+    const float4 s = sum_slots4<RED_TX, RED_TY>(gp, n_slots, total, i4, in_range);
     if (threadIdx.y == 0) {
         if (in_range)
             for (int p = 0; p < pa.world; ++p)
                 reinterpret_cast<float4*>(pa.data[p] + ((size_t)buf * pa.world + pa.rank) * row)[i4] = s;
         __threadfence_system();
         __syncwarp();
-        if (lane < pa.world) st_release_sys(pa.flags[lane] + (size_t)pa.rank * (pa.n_cta + 1) + blockIdx.x, seq);
-        if (lane < pa.world) wait_flag(pa.flags[pa.rank] + (size_t)lane * (pa.n_cta + 1) + blockIdx.x, seq, pa.err);
+        if (lane < pa.world) st_release_sys(pa.flags[lane] + (size_t)pa.rank * (pa.n_cta + 1) + sl, seq);
+        if (lane < pa.world) wait_flag(pa.flags[pa.rank] + (size_t)lane * (pa.n_cta + 1) + sl, seq, pa.err);
         __syncwarp();
         if (in_range) {
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -223,7 +226,7 @@ __global__ void reduce_peer_adam_kernel(const float* __restrict__ gp, const floa
                 reinterpret_cast<float4*>(v)[i4] = vv;
             }
         }
-    } else if (blockIdx.x == 0 && threadIdx.y == 1) {          // the 8 loss terms ride the same exchange (flag column n_cta)
+    } else if (sl == 0 && threadIdx.y == 1) {          // the 8 loss terms ride the same exchange (flag column n_cta)
         float st = 0.f;
         if (lane < PE_MAX_TERMS) {
             for (int k = 0; k < n_slots; ++k) st += __ldcg(tp + (size_t)k * PE_MAX_TERMS + lane);
@@ -241,7 +244,8 @@ __global__ void reduce_peer_adam_kernel(const float* __restrict__ gp, const floa
             if (tcopy) tcopy[lane] = g;
         }
     }
-    __syncthreads();
+    __syncthreads();                 // the shared partial-sum array of sum_slots4 is reused by the next slice
+    }
     if (do_adam && threadIdx.x == 0 && threadIdx.y == 0) {
         __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
@@ -387,7 +391,8 @@ extern "C" int pe_reduce_peer(const pe_plan* plan, pe_comm* c, const float* d_gr
     const int total = plan->lay.total;
     dim3 bs(RED_TX, RED_TY);
     const int do_adam = d_params != nullptr;
-    cudaError_t e = pe_launch_pdl(reduce_peer_adam_kernel, dim3(c->n_cta), bs, 0, (cudaStream_t)stream, d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
+    const int grid = c->n_cta < plan->sms ? c->n_cta : plan->sms;      // co-resident by construction (1,024-thread blocks: one per SM)
+    cudaError_t e = pe_launch_pdl(reduce_peer_adam_kernel, dim3(grid), bs, 0, (cudaStream_t)stream, d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
                                   d_params, d_m, d_v, d_step, do_adam ? reinterpret_cast<unsigned int*>(d_step + 1) : nullptr,
                                   lr, beta1, beta2, eps, pa, c->seq, do_adam);
     if (e == cudaSuccess) e = cudaGetLastError();

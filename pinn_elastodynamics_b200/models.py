@@ -165,6 +165,8 @@ class _Base:
                     if it + 1 < iters:
                         upload(1 - cur)
                 eng.adam_step(learning_rate, hist[it])                 # hist[it] = terms BEFORE update it
+                if eng.comm is not None and (it + 1) % 1000 == 0:
+                    eng.check_comm()                                   # a peer that timed out must not go unnoticed for the rest of a long run
                 if refeed:
                     used_done[cur].record(main)
                     host_rows[cur].copy_(hist[it], non_blocking=True)
