@@ -223,6 +223,9 @@ int pe_vec_dot_max(int n, const float *d_a, const float *d_b, float *d_res, void
  * epilogue thread 0, 16..31 phases of the MMA/TMA issuer of CTA 0 (tests/tcf_gpu_check.py prof; selects the profiling instantiation). */
 void pe_debug_set_tcs_profile(unsigned long long *d_counters32);     /* PE_ENGINE_TCS_* */
 void pe_debug_set_tcf_profile(unsigned long long *d_counters32);     /* PE_ENGINE_TCF */
+/* engine of pe_forward_fields: PE_ENGINE_TCF (default: batches of >= 512 points of networks the tensor-core engine supports run its forward
+ * sweep, everything else the SIMT kernel), PE_ENGINE_SIMT_FP32, or -1 = re-read $PE_FIELDS_ENGINE ("simt" | "tcf") at the next call */
+void pe_debug_set_fields_engine(int engine);
 
 #ifdef __cplusplus
 }

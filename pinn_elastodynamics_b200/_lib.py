@@ -83,6 +83,7 @@ SYMBOLS = [
     ('pe_vec_dot_max', _i, [_i, _vp, _vp, _vp, _vp]),
     ('pe_debug_set_tcs_profile', None, [_vp]),
     ('pe_debug_set_tcf_profile', None, [_vp]),
+    ('pe_debug_set_fields_engine', None, [_i]),
 ]
 
 _lib = None

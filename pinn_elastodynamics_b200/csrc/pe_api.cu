@@ -120,7 +120,10 @@ extern "C" pe_plan* pe_plan_create(const int* dims, int n_dims, int device) {
     return p;
 }
 
-extern "C" void pe_plan_destroy(pe_plan* plan) { delete plan; }
+extern "C" void pe_plan_destroy(pe_plan* plan) {
+    if (plan && plan->d_tc_images) cudaFree(plan->d_tc_images);
+    delete plan;
+}
 extern "C" int pe_plan_param_count(const pe_plan* plan) { return plan ? plan->lay.compact : -1; }
 extern "C" int pe_plan_param_count_padded(const pe_plan* plan) { return plan ? plan->lay.total : -1; }
 extern "C" int pe_plan_weight_offset(const pe_plan* plan, int l) { return (plan && l >= 0 && l < plan->lay.L) ? plan->lay.woff[l] : -1; }
@@ -278,6 +281,11 @@ extern "C" int pe_residual_loss_grad_fused(const pe_plan* plan, const pe_term_de
                            d_params, d_grad_partials, d_term_partials, d_stash, slot_base, stream);
 }
 
+// engine of pe_forward_fields: PE_ENGINE_TCF (default; batches of >= 512 points of networks the tensor-core engine supports) or PE_ENGINE_SIMT_FP32;
+// -1 = take $PE_FIELDS_ENGINE at the next call
+static int g_fields_engine = -1;
+extern "C" void pe_debug_set_fields_engine(int engine) { g_fields_engine = engine; }
+
 extern "C" int pe_forward_fields(const pe_plan* plan, int formulation, const float* d_points, int ld, int n,
                                  const float* in_scale, const float* in_shift, const float* d_aux, int aux_k,
                                  const float* d_params, float* d_out, void* stream) {
@@ -293,6 +301,11 @@ extern "C" int pe_forward_fields(const pe_plan* plan, int formulation, const flo
     a.points = d_points; a.aux = d_aux; a.params = d_params; a.out = d_out;
     a.n = n; a.ld = ld; a.aux_k = aux_k; a.mode = 0; a.formulation = formulation;
     for (int i = 0; i < 3; ++i) { a.in_scale[i] = in_scale ? in_scale[i] : 1.f; a.in_shift[i] = in_shift ? in_shift[i] : 0.f; }
+    // tensor-core forward sweep for frame batches (the reference predicts 251 x 251 x 81 points, plate:980-998); small batches, wide nets and
+    // PE_FIELDS_ENGINE=simt take the fp32 SIMT kernel
+    if (g_fields_engine < 0) { const char* e = getenv("PE_FIELDS_ENGINE"); g_fields_engine = (e && strcmp(e, "simt") == 0) ? PE_ENGINE_SIMT_FP32 : PE_ENGINE_TCF; }
+    if (g_fields_engine == PE_ENGINE_TCF && n >= 4 * PE_TC_TILE && plan->lay.L >= 3 && tcgen_supported(plan, formulation == PE_RES_F5 ? 5 : 4))
+        return pe_launch_fields_tcf(plan, a, (cudaStream_t)stream);
     return pe_launch_fields(plan, a, 4, (cudaStream_t)stream);
 }
 

@@ -32,6 +32,7 @@ struct pe_plan {
     int device;
     int sms;
     int smem_optin;
+    void* d_tc_images = nullptr;   // operand images of the tensor-core predict path (csrc/pe_tcf.cu pe_launch_fields_tcf), allocated at first use
 };
 
 struct PeResidArgs {
@@ -93,6 +94,7 @@ static inline cudaError_t pe_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 
 // launchers (defined in the .cu files)
 int pe_launch_resid_simt(const pe_plan* plan, const PeResidArgs& a, int K, int slots, cudaStream_t st);
 int pe_launch_fields(const pe_plan* plan, const PeFieldsArgs& a, int K, cudaStream_t st);
+int pe_launch_fields_tcf(const pe_plan* plan, const PeFieldsArgs& a, cudaStream_t st);
 int pe_simt_smem_bytes(const PeLayout& lay, int K);
 bool pe_simt_stage_weights(const pe_plan* plan, int K);
 int pe_simt_ctas_per_sm(const pe_plan* plan, int K);

@@ -7,40 +7,47 @@
 namespace {
 
 #define RED_TX 32      // peer-memory kernel: float4 columns per block (one arrival flag per block and peer: few, wide blocks)
-#define RED_TY 32      //                     slot groups per block -- the SAME count as RA_TY: the summation order over the slots depends on it
-                       //                     alone, and the peer path must stay bit-identical to reduce -> NCCL all-reduce -> Adam
-#define RA_TX 8        // single-GPU kernels: 8 float4 columns (one 128-byte line per slot) x 32 slot groups per block -> four times the blocks
+#define RED_TY 16      //                     slot-group rows per block
+#define RA_TX 8        // single-GPU kernels: 8 float4 columns (one 128-byte line per slot) x 32 rows per block -> four times the blocks
 #define RA_TY 32       // (360 for the 5x50 net): the reduction is a latency chain of L2 loads, more CTAs in flight shorten it
+#define RED_NP 32      // canonical partial sums per column: partial j = slots j, j + 32, j + 64, ... added in increasing order
 
-// blockDim = (TX, TY).  Thread (tx, ty) sums slots ty, ty+TY, ... of float4 column i4 (4 loads in flight), the TY partials are
-// then added in a fixed order (groups of 8, then the group sums, by ty == 0): deterministic for a given n_slots.
+// blockDim = (TX, TY), TY divides RED_NP.  The summation ORDER is independent of the block shape: 32 partial sums per column (slot index
+// mod 32), then groups of 8 partials, then the 4 group sums -- so the single-GPU kernels, the NCCL path and the peer-memory kernel produce
+// the same bits for the same slots.  Thread (tx, ty) owns partials ty, ty + TY, ...; all its loads are in flight together.
 template <int TX, int TY>
 __device__ __forceinline__ float4 sum_slots4(const float* __restrict__ partials, int n_slots, int stride, int i4, bool in_range) {
-    __shared__ float4 red[TY][TX];
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in_range) {
-        const float4* p = reinterpret_cast<const float4*>(partials) + i4;
-        const size_t stride4 = (size_t)(stride >> 2);
-        int k = threadIdx.y;
-        for (; k + 3 * TY < n_slots; k += 4 * TY) {
-            float4 a = __ldcg(p + (size_t)(k) * stride4);
-            float4 b = __ldcg(p + (size_t)(k + TY) * stride4);
-            float4 c = __ldcg(p + (size_t)(k + 2 * TY) * stride4);
-            float4 d = __ldcg(p + (size_t)(k + 3 * TY) * stride4);
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-            s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
-            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+    constexpr int PER = RED_NP / TY;
+    __shared__ float4 red[RED_NP][TX];
+    const float4* p = reinterpret_cast<const float4*>(partials) + i4;
+    const size_t stride4 = (size_t)(stride >> 2);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int j = threadIdx.y + q * TY;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_range) {
+            int k = j;
+            for (; k + 3 * RED_NP < n_slots; k += 4 * RED_NP) {
+                float4 a = __ldcg(p + (size_t)(k) * stride4);
+                float4 b = __ldcg(p + (size_t)(k + RED_NP) * stride4);
+                float4 c = __ldcg(p + (size_t)(k + 2 * RED_NP) * stride4);
+                float4 d = __ldcg(p + (size_t)(k + 3 * RED_NP) * stride4);
+                s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+                s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+                s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+                s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+            }
+            for (; k < n_slots; k += RED_NP) {
+                float4 a = __ldcg(p + (size_t)k * stride4);
+                s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            }
         }
-        for (; k < n_slots; k += TY) {
-            float4 a = __ldcg(p + (size_t)k * stride4);
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-        }
+        red[j][threadIdx.x] = s;
     }
-    red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
-    constexpr int G = 8;                        // rows ty < TY / G each add the G partials ty * G .. ty * G + G - 1
-    if (threadIdx.y < TY / G) {
+    constexpr int G = 8;                        // rows ty < RED_NP / G each add the G partials ty * G .. ty * G + G - 1
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.y < RED_NP / G) {
         s = red[threadIdx.y * G][threadIdx.x];
 #pragma unroll
         for (int r = 1; r < G; ++r) {
@@ -49,11 +56,11 @@ __device__ __forceinline__ float4 sum_slots4(const float* __restrict__ partials,
         }
     }
     __syncthreads();
-    if (threadIdx.y < TY / G) red[threadIdx.y][threadIdx.x] = s;
+    if (threadIdx.y < RED_NP / G) red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0) {
 #pragma unroll
-        for (int r = 1; r < TY / G; ++r) {
+        for (int r = 1; r < RED_NP / G; ++r) {
             float4 a = red[r][threadIdx.x];
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
@@ -182,7 +189,7 @@ __device__ __forceinline__ void wait_flag(const unsigned int* p, unsigned int se
     }
 }
 
-__global__ void reduce_peer_adam_kernel(const float* __restrict__ gp, const float* __restrict__ tp, int n_slots, int total, float* __restrict__ out,
+__global__ void __launch_bounds__(RED_TX * RED_TY) reduce_peer_adam_kernel(const float* __restrict__ gp, const float* __restrict__ tp, int n_slots, int total, float* __restrict__ out,
                                         float* __restrict__ tcopy, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
                                         int* __restrict__ d_step, unsigned int* __restrict__ ticket, float lr, float b1, float b2, float eps,
                                         PeerArgs pa, unsigned int seq, int do_adam) {
@@ -391,7 +398,7 @@ extern "C" int pe_reduce_peer(const pe_plan* plan, pe_comm* c, const float* d_gr
     const int total = plan->lay.total;
     dim3 bs(RED_TX, RED_TY);
     const int do_adam = d_params != nullptr;
-    const int grid = c->n_cta < plan->sms ? c->n_cta : plan->sms;      // co-resident by construction (1,024-thread blocks: one per SM)
+    const int grid = c->n_cta < plan->sms ? c->n_cta : plan->sms;      // co-resident by construction (at least one 512-thread block per SM)
     cudaError_t e = pe_launch_pdl(reduce_peer_adam_kernel, dim3(grid), bs, 0, (cudaStream_t)stream, d_grad_partials, d_term_partials, n_slots, total, d_out, d_terms_copy,
                                   d_params, d_m, d_v, d_step, do_adam ? reinterpret_cast<unsigned int*>(d_step + 1) : nullptr,
                                   lr, beta1, beta2, eps, pa, c->seq, do_adam);

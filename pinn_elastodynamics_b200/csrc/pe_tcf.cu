@@ -217,6 +217,8 @@ struct TcfArgs {
     int fast;                   // 1 = 16-bit forward mode: forward layer GEMMs as single fp16 products (adjoint / weight-gradient GEMMs stay fp16 pairs)
     unsigned long long* prof;   // PROF instantiation: 32 cycle counters (0..15 epilogue thread 0, 16..31 issuer) of CTA prof_cta
     int prof_cta;               // $PE_PROF_CTA (default 0)
+    float* fields_out;          // FWD instantiation (forward sweep only, `predict`): [n][8] = u, v, s11, s22, s12, e11, e22, e12
+    int fields_aux_k;           // ... composite u = P + D N on the (value, x, y, t) streams: r.aux = [n][2][4][5] (0: plain outputs)
 };
 
 #define TCF_PROF(slot) do { if (PROF) { if (prof_on) { const long long now_ = clock64(); atomicAdd(args.prof + (slot), (unsigned long long)(now_ - prof_t)); prof_t = now_; } } } while (0)
@@ -262,7 +264,9 @@ __device__ __forceinline__ void issue_group(uint32_t tbase, uint32_t a_lo, uint3
         }
 }
 
-template <int NS, bool PROF>
+// FWD: forward sweep only (the reference's predict, plate:449-461: u, v, stresses and strains of a point batch) -- no stash, no seeds, no
+// reverse sweep; the output stage writes the eight fields of every point.
+template <int NS, bool PROF, bool FWD>
 __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs args) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int STASH_LAYER = NS * F_STREAM;                 // bytes per stashed layer: NS x (hi plane | lo plane)
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
     float* gpart = A.grad_partials + (size_t)slot * lay.total;
     uint8_t* stash = reinterpret_cast<uint8_t*>(A.stash + (size_t)blockIdx.x * A.stash_floats);
     const float* __restrict__ params = A.params;
-    for (int i = tid; i < lay.total; i += F_THREADS) __stcg(gpart + i, 0.f);
+    if (!FWD) for (int i = tid; i < lay.total; i += F_THREADS) __stcg(gpart + i, 0.f);
     __syncthreads();
     for (int i = tid; i < 512; i += F_THREADS) reinterpret_cast<__half*>(smem + F_ONES)[i] = __float2half_rn(1.f);
     if (tid < 64) {                                  // first-layer weights (3 x d1) and bias -> smem, once per launch
@@ -395,6 +399,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 // ---------------------------------------------------------------- reverse sweep: layers L..2
                 // the region F_R changes hands: wait until the output-layer MMAs (the last readers of a forward image) are complete
                 mbar_wait(bar_acc + 16, (n_acc2 - 1) & 1u);
+                if (FWD) {                                   // forward only: the image buffers go back to layers 2 and 3 of the next tile
+                    if (tile + (int)gridDim.x < ntiles) {
+                        load_fwd(2);
+                        if (L >= 3) load_fwd(3);
+                    }
+                    continue;
+                }
                 mbar_expect_tx(bar_img, F_IMG);
                 tma_load_1d(r_s, adj_src(L), F_IMG, bar_img);
                 mbar_arrive(bar_revgo);                      // the second issuer may start this tile's gradient phases (the staging slots are free)
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                 }
             }
         }
-        else if (warp == F_CTRL + 1 && lane == 0) {
+        else if (!FWD && warp == F_CTRL + 1 && lane == 0) {
             // ---------------------------------------------------------------- second issuer: weight / bias gradient phases of the reverse sweep
             uint32_t pact = 0, psfull = 0, psfree = 0, pdrained = 1, prevgo = 0, n_dw = 0;
             auto wait_act = [&](int g) { mbar_wait(bar_act + 8 * g, (pact >> g) & 1u); pact ^= 1u << g; };
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     if (npt < (nsec ? args.n2 : A.n)) {
                         const float* nrow = (nsec ? args.points2 : A.points) + (size_t)npt * (nsec ? T2.ld : T.ld);
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
-                        if (!nsec && A.aux) {
+                        if (!FWD && !nsec && A.aux) {
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(A.aux + (size_t)npt * 50));
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(A.aux + (size_t)npt * 50 + 32));
                         }
@@ -651,7 +662,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     }
 #pragma unroll
                     for (int k = 0; k < NS; ++k)
-                        if (k == 0 || !sec) put4(stash, k, c4, o[k][0], o[k][1]);      // stash layer 0 = outputs of layer 1
+                        if (k == 0 || !sec) put4(FWD ? nullptr : stash, k, c4, o[k][0], o[k][1]);      // stash layer 0 = outputs of layer 1
                 }
                 publish_fences();
                 publish(0); publish(1); publish(2);
@@ -661,7 +672,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
             for (int l = 2; l < L; ++l) {
                 const int lo4 = c4_lo(lay.d[l]), hi4 = c4_hi(lay.d[l]);
                 const float* bl = sbias + (l - 1) * 64;
-                uint8_t* st = stash + (size_t)(l - 1) * STASH_LAYER;
+                uint8_t* st = FWD ? nullptr : stash + (size_t)(l - 1) * STASH_LAYER;
                 // ---- G0: a = tanh(z_0 + b)      (pad units: zero weight columns and bias -> exactly 0)
                 wait_acc(0);
                 TCF_PROF(1);
@@ -742,6 +753,24 @@ TCF_PRAGMA(unroll TCF_FWD_UNROLL)
                     }
 #pragma unroll
                     for (int u = 0; u < PE_UJ; ++u) if (u < dout) Y[0][u] += bl[u];
+                    if (FWD) {                       // predict: fields of this point (same composition and column order as fields_simt_kernel)
+                        if (valid) {
+                            if (args.fields_aux_k) {       // composite on (value, x, y, t) streams, 5 outputs (plate:382-387)
+                                const float* ar = A.aux + (size_t)pt * (2 * args.fields_aux_k * 5);
+#pragma unroll
+                                for (int o = 0; o < 5; ++o) {
+                                    const float D0 = ar[o], N0 = Y[0][o];
+#pragma unroll
+                                    for (int k = 2; k >= 1; --k) Y[k][o] = ar[args.fields_aux_k * 5 + k * 5 + o] + ar[k * 5 + o] * N0 + D0 * Y[k][o];
+                                    Y[0][o] = fmaf(D0, N0, ar[args.fields_aux_k * 5 + o]);
+                                }
+                            }
+                            const bool f7 = T.kind == PE_RES_F7;
+                            float4* o4 = reinterpret_cast<float4*>(args.fields_out + (size_t)pt * 8);
+                            o4[0] = make_float4(Y[0][0], Y[0][1], f7 ? Y[0][4] : Y[0][2], f7 ? Y[0][5] : Y[0][3]);
+                            o4[1] = make_float4(f7 ? Y[0][6] : Y[0][4], Y[1][0], Y[2][1], Y[2][0] + Y[1][1]);      // e11 = u_x, e22 = v_y, e12 = u_y + v_x (plate:393-395)
+                        }
+                    } else
                     if (!sec) {
                         const float* aux_row = (NS == 5 && A.aux) ? A.aux + (size_t)(valid ? pt : 0) * 50 : nullptr;
                         residual_stage<NS>(Y, T, aux_row, row, valid, A.inv_n, tsum);
@@ -766,6 +795,7 @@ TCF_PRAGMA(unroll TCF_FWD_UNROLL)
                     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
                     if (lane == 0) tile_scale[warp] = amax;
                 }
+                if (FWD) { TCF_PROF(8); continue; }          // next tile (its layer-1 planes are written behind the barrier at the tile start)
                 // the tile's seed scale: sigma = 2^-e with max |seed| * sigma in [1, 2)  (1 when all seeds vanish); identical in every thread
                 named_bar_sync(1, F_EPI);
                 const float m4 = fmaxf(fmaxf(tile_scale[0], tile_scale[1]), fmaxf(tile_scale[2], tile_scale[3]));
@@ -1016,7 +1046,7 @@ TCF_PRAGMA(unroll TCF_FWD_UNROLL)
             TCF_PROF(13);
         }
         // ---- loss-term partial sums (threads with h == 0 hold them): warp reduce, then 4 warps through smem (fixed order)
-        {
+        if (!FWD) {
             float tot[2 + PE_MAX_TERMS];
             tot[0] = warp_sum(tsum[0]);
             tot[1] = warp_sum(tsum[1]);
@@ -1047,9 +1077,9 @@ TCF_PRAGMA(unroll TCF_FWD_UNROLL)
     if (warp == F_CTRL) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
-template <int NS, bool PROF>
+template <int NS, bool PROF, bool FWD = false>
 int launch_tcf(const TcfArgs& t, int slots, cudaStream_t st) {
-    auto kern = resid_tcf_kernel<NS, PROF>;
+    auto kern = resid_tcf_kernel<NS, PROF, FWD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F_TOTAL);
     if (e != cudaSuccess) { pe_set_error("cudaFuncSetAttribute(resid_tcf, %d): %s", F_TOTAL, cudaGetErrorString(e)); return 2; }
     e = pe_launch_pdl(kern, dim3(slots), dim3(F_THREADS), F_TOTAL, st, t);
@@ -1080,6 +1110,7 @@ int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int fa
     if (plan->lay.L < 3) { pe_set_error("tcf engine: needs at least two hidden layers"); return 1; }
     t.prof = g_tcf_prof;
     { const char* e = getenv("PE_PROF_CTA"); t.prof_cta = e ? atoi(e) : 0; }
+    t.fields_out = nullptr; t.fields_aux_k = 0;
     t.fast = fast;
     t.r.stash_floats = (int)pe_tc_stash_floats_per_slot(plan);
     uint8_t* images = reinterpret_cast<uint8_t*>(a.stash + (size_t)slots * t.r.stash_floats);
@@ -1091,4 +1122,32 @@ int pe_launch_resid_tcf(const pe_plan* plan, const PeResidArgs& a, int K, int fa
     if (K == 4) return g_tcf_prof ? launch_tcf<4, true>(t, slots, st) : launch_tcf<4, false>(t, slots, st);
     pe_set_error("tcf engine: K = %d not instantiated (4 or 5)", K);
     return 1;
+}
+
+// ---- predict on the tensor-core engine: forward sweep of the four streams (value, d/dx, d/dy, d/dt) in 128-point tiles, fields written by
+// the output stage.  The operand images live in a buffer owned by the plan (allocated at the first call).  Same contract as the SIMT fields
+// kernel (pe_launch_fields, mode 0); hidden widths <= 56 and at least two hidden layers.
+int pe_launch_fields_tcf(const pe_plan* plan, const PeFieldsArgs& a, cudaStream_t st) {
+    const PeLayout& lay = plan->lay;
+    pe_plan* mp = const_cast<pe_plan*>(plan);
+    if (!mp->d_tc_images) {
+        cudaError_t e = cudaMalloc(&mp->d_tc_images, (size_t)lay.L * F_IMG_LAYER);
+        if (e != cudaSuccess) { pe_set_error("tcf fields: cudaMalloc(operand images): %s", cudaGetErrorString(e)); mp->d_tc_images = nullptr; return 2; }
+    }
+    TcfArgs t;
+    memset(&t, 0, sizeof(t));
+    t.r.lay = lay;
+    t.r.term.kind = a.formulation;
+    t.r.term.ld = a.ld;
+    for (int i = 0; i < 3; ++i) { t.r.term.in_scale[i] = a.in_scale[i]; t.r.term.in_shift[i] = a.in_shift[i]; }
+    t.r.points = a.points; t.r.aux = a.aux; t.r.params = a.params;
+    t.r.n = a.n;
+    t.images = static_cast<const uint8_t*>(mp->d_tc_images);
+    t.fields_out = a.out; t.fields_aux_k = a.aux_k;
+    cudaError_t e = pe_launch_pdl(tcf_image_kernel, dim3(lay.L * 16), dim3(256), 0, st, a.params, lay, static_cast<uint8_t*>(mp->d_tc_images));
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { pe_set_error("tcf_image_kernel: %s", cudaGetErrorString(e)); return 3; }
+    const int ntiles = (a.n + TC_P - 1) / TC_P;
+    const int ctas = ntiles < plan->sms ? ntiles : plan->sms;
+    return launch_tcf<4, false, true>(t, ctas, st);
 }

@@ -147,6 +147,36 @@ def prof(flush):
         del m
 
 
+def fields(flush):
+    """predict of a frame batch (2 M points, 5x50 plate net): SIMT fields kernel against the tensor-core forward sweep"""
+    layers = [3] + 5 * [50] + [5]
+    Collo, HOLE = bench.make_workload(2000)
+    m = pe.PINN(Collo, HOLE, None, None, None, None, None, None, layers, None, None, None, None, verbose=False, engine='tcf')
+    Ws, bs = xavier_init_lists(layers, np.random.default_rng(1111))
+    m.uv_net.set_weights(Ws, bs)
+    n = 2_000_000
+    pts = torch.rand((n, 3), device='cuda') * torch.tensor([0.5, 0.5, 10.0], device='cuda')
+    ref = None
+    for name, eng in (('simt', L.ENGINE_SIMT_FP32), ('tcf', L.ENGINE_TCF)):
+        lib.pe_debug_set_fields_engine(eng)
+        for _ in range(3):
+            out = m.uv_net.forward_fields(pts, m.formulation)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = m.uv_net.forward_fields(pts, m.formulation); e1.record()
+            torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        o = out.cpu().numpy().astype(np.float64)
+        row = dict(case='fields', engine=name, points=n, ms=float(np.median(ts)), mpts_per_s=n / float(np.median(ts)) / 1e3, hbm_gbs=n * 44 / float(np.median(ts)) / 1e6)
+        if ref is None:
+            ref = o
+        else:
+            row['max_rel_vs_simt'] = [float(np.abs(o[:, c] - ref[:, c]).max() / max(1.0, np.abs(ref[:, c]).max())) for c in range(8)]
+        emit(**row)
+    lib.pe_debug_set_fields_engine(-1)
+
+
 if __name__ == '__main__':
     T0 = time.time()
     assert torch.cuda.is_available()
@@ -155,5 +185,5 @@ if __name__ == '__main__':
     what = sys.argv[1:] or ['f5', 'f7']
     emit(case='start', what=what, engines=ENGINES, device=torch.cuda.get_device_name(0))
     for w in what:
-        {'f5': f5, 'f7': f7, 'prof': prof}[w](flush)
+        {'f5': f5, 'f7': f7, 'prof': prof, 'fields': fields}[w](flush)
     emit(case='done')
