@@ -492,15 +492,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) resid_tcf_kernel(const TcfArgs a
                     //      size, is what the tensor pipe charges for at these shapes (tests/probe_umma_timing.py: ~64 cycles per instruction up to N = 128).
                     // the gradient tiles of the previous layer (or tile) must have been drained before they are overwritten; the epilogue warps
                     // publish Zbar first and drain afterwards, behind the adjoint MMAs issued above
+                    TCF_PROF(27);
                     mbar_wait(bar_drained, pdrained);
                     pdrained ^= 1u;
+                    TCF_PROF(30);
                     const int nzc = (dout + 7) >> 3;        // unit chunks of Zbar_l that hold data
                     const uint32_t id112 = idesc_mn(112), idz = idesc_mn(8 * nzc), id8 = idesc_mn(8);
 #pragma unroll 1
                     for (int k = 0; k < nst; ++k) {
                         const uint32_t sb = (uint32_t)(k & 1);
+                        if (k == 0) TCF_PROF(27);
                         mbar_wait(bar_sfull + 8 * sb, (psfull >> sb) & 1u);
                         psfull ^= 1u << sb;
+                        if (k == 0) TCF_PROF(31);
                         const uint32_t ga = g_lo + sb * (uint32_t)(F_STREAM >> 4);
                         const uint32_t zh = z_lo + (uint32_t)k * (uint32_t)(F_STREAM >> 4), zl = zh + (uint32_t)(F_PLANE >> 4);
 #pragma unroll
@@ -857,8 +861,11 @@ TCF_PRAGMA(unroll TCF_FWD_UNROLL)
 #pragma unroll
                     for (int k = 0; k < NS; ++k) {
                         const uint32_t sb = (uint32_t)(k & 1);
+                        if (k <= 1) TCF_PROF(10);
                         mbar_wait(bar_sdone + 8 * sb, (psdone >> sb) & 1u);
                         psdone ^= 1u << sb;
+                        if (k == 0) TCF_PROF(14);    // from the end of the previous drain to the first stream's weight-gradient MMAs complete
+                        if (k == 1) TCF_PROF(15);    // ... the second stream's
                         const uint8_t* slot = smem + F_STG + sb * F_STREAM;
                         // this thread's entries of the slot -> registers, then the slot is released at once (the bulk copy of stream k + 2 is the
                         // longest link of the per-slot chain copy -> MMAs -> pass; the arithmetic below runs while it is in flight)

@@ -116,10 +116,10 @@ def f7(flush):
 
 
 TCF_NAMES = ['E: tile start + layer1 fwd', 'E: fwd wait ACC[G0]', 'E: fwd epilogue G0 (tanh)', 'E: fwd wait ACC[G1]', 'E: fwd epilogue G1 (x,y)', 'E: fwd wait ACC[G2]',
-             'E: fwd epilogue G2 (t,tt)', 'E: output layer wait', 'E: output/residual stage', 'E: rev wait adjoint MMAs', 'E: rev stream passes (waits + work)',
-             'E: rev wait dW MMAs', 'E: dW drain + publish', 'E: layer1 grad', '-', '-',
+             'E: fwd epilogue G2 (t,tt)', 'E: output layer wait', 'E: output/residual stage', 'E: rev wait ACC[G1] (after the slot reads of streams 0, 1)', 'E: rev stream passes (waits + work)',
+             'E: rev wait dW MMAs', 'E: dW drain + publish', 'E: layer1 grad', 'E: rev wait SDONE[stream 0]', 'E: rev wait SDONE[stream 1]',
              'I: fwd wait image', 'I: fwd wait ACT[G0]', 'I: fwd issue G0', 'I: fwd wait ACT[G1]', 'I: fwd issue G1', 'I: fwd wait ACT[G2]', 'I: fwd issue G2',
-             'I: fwd wait prev layer + TMA', 'I: rev wait image', 'I: rev wait ACT', 'I: adjoint issue', 'I: dW loop (waits + issue)', 'I: wait dW done + slots free', 'I: layer-1 gradient (wait + MMAs)', '-', '-']
+             'I: fwd wait prev layer + TMA', 'I: rev wait image', 'I: rev wait ACT', 'I: adjoint issue', 'I2: wait ACT + dW loop (other waits + issue)', 'I: wait dW done + slots free', 'I: layer-1 gradient (wait + MMAs)', 'I2: wait DRAINED (after ACT)', 'I2: wait SFULL[stream 0] (bulk copy landed)']
 
 
 def prof(flush):

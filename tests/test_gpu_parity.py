@@ -433,7 +433,7 @@ def test_full_size_50k_parity_and_shard_additivity(pe, engine):
 def test_plate_recipe_end_to_end(pe, golden):
     """The reference driver's sequence on a shrunken problem: sample point sets -> PINN -> train_bfgs_dist -> train_bfgs_part ->
     Adam -> L-BFGS -> save/load -> frame-batched predict -> FEM metrics (plate:892-998).  Checks that every stage runs, the loss
-    decreases, and that predict_frames (one launch) equals per-frame predict (the reference's loop)."""
+    decreases, and that predict_frames (one launch) agrees with per-frame predict (the reference's loop)."""
     from pinn_elastodynamics_b200 import preprocess as P
     S = P.plate_point_sets(rng=np.random.default_rng(11), scale=0.01)
     uv, dl, pl = [3, 30, 30, 30, 5], [3, 10, 10, 5], [3, 10, 10, 5]
@@ -454,7 +454,7 @@ def test_plate_recipe_end_to_end(pe, golden):
     frames = m.predict_frames(A[:, 0:1], A[:, 1:2], times)
     for t, fr in zip(times, frames):
         one = m.predict(A[:, 0:1], A[:, 1:2], np.full((A.shape[0], 1), t))
-        for a, b in zip(fr, one):
-            np.testing.assert_array_equal(a, b)
+        for a, b in zip(fr, one):       # 1,200 points in one launch run the tensor-core forward sweep, 400 per frame the SIMT fields kernel: fields bar
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-5 * max(1.0, np.abs(b).max()))
     met = P.fem_metrics(frames[1][:5], [A[:, 2 + i] for i in range(5)])
     assert set(met) == {'u', 'v', 's11', 's22', 's12'} and all(np.isfinite(list(met.values())))
