@@ -16,17 +16,24 @@
 // Layout.  Activation planes, per stream  [hi: 7 chunks of 8 units][128 points][8 x fp16] | [lo: same]  = 28,672 B: K-major operand of
 // the layer GEMMs (LBO 2,048, SBO 128; the fourth K-step's second chunk is whatever follows the plane -- finite 16-bit patterns --
 // against weight rows 56..63 that are zero) and, read MN-major, the [Zh | Zl] operand (N = 112) of the weight-gradient GEMM.  The forward
-// epilogue stashes the planes as they are (4 B per element) and the issuer brings them back with one bulk-TMA copy per stream: no
-// conversion pass.  Tensor memory: 5 x 64 accumulator columns | weight-gradient tile, 64 lanes x (56 hi-hi | 56 cross) | bias tile 8 + 8.
+// epilogue stashes the planes as they are (4 B per element) and the second issuer brings them back with one bulk-TMA copy per stream: no
+// conversion pass.  Tensor memory (columns): 5 x 64 accumulators | weight-gradient tile 112 (rows 0..55: Ah^T [Zh | Zl], rows 56..111:
+// Al^T Zh) | bias tile 8 | layer-1 gradient tiles 4 x 8 (value stream x coordinate block, column sums of d/dx, d/dy, d/dt).
 //
-// Roles (warp-specialised as in the third generation): F_EW epilogue warps (thread (p, h): TMEM lane p = point, unit group h), one
-// control warp whose lane 0 issues every tcgen05.mma / commit / bulk copy.  Forward: the jet streams travel as three groups
-// G0 = {value}, G1 = {d/dx, d/dy}, G2 = {d/dt[, d2/dt2]} with ACT[g] / ACC[g] mbarrier pairs, so the tensor pipe runs G1 / G2 of a layer
-// while the epilogue warps apply tanh to G0.  Reverse, per layer l:
-//   issuer : adjoint image landed, Zbar_l published -> adjoint MMAs -> commit ACC -> per stream k: stashed planes of A_{l-1,k} landed in
-//            staging buffer k & 1 -> 8 K-steps of 16 points x {Ah x [Zh|Zl], Al x Zh} into the weight-gradient tile -> commit EMPTY -> refill;
-//            Zh^T 1, Zl^T 1 into the bias tile -> commit DW
-//   epilogue warps: wait ACC, DW -> drain both tiles into this CTA's gradient slot -> adjoint of tanh -> Zbar_{l-1} planes -> publish.
+// Roles (warp-specialised): F_EW epilogue warps (thread (p, h): TMEM lane p = point, unit group h) and one control warpgroup with two issuing
+// threads -- issuer 1: every forward / adjoint tcgen05.mma, their commits, the operand-image bulk copies; issuer 2: the stash bulk copies and
+// the weight / bias / layer-1 gradient MMAs.  Forward: the jet streams travel as three groups G0 = {value}, G1 = {d/dx, d/dy},
+// G2 = {d/dt[, d2/dt2]} with ACT[g] / ACC[g] mbarrier pairs, so the tensor pipe runs G1 / G2 of a layer while the epilogue warps apply tanh
+// to G0.  Reverse, per layer l:
+//   issuer 1: adjoint image landed, Zbar_l group published -> adjoint MMAs of that group (G1, G2, G0: the order the passes consume them) -> commit
+//   issuer 2: per stream k: stashed planes of A_{l-1,k} landed in staging slot k & 1 -> 8 K-steps of 16 points x {Ah x [Zh|Zl], Al x Zh} into the
+//             weight-gradient tile -> commit SDONE[slot] -> refill the slot once the epilogue warps have read it; Zh^T 1, Zl^T 1 into the bias
+//             tile with the last stream -> commit DW; after layer 2: the layer-1 gradient MMAs -> commit L1
+//   epilogue warps: per stream k: wait SDONE (and the stream's adjoint group) -> A_{l-1,k} from the slot, abar_k from tensor memory -> Zbar_{l-1,k}
+//             over the Zbar_l,k plane -> publish (G1 early in the five-stream kernel); then wait DW -> drain both tiles into this CTA's gradient slot.
+// FWD instantiation: forward sweep only (predict): no stash, the output stage writes the eight fields of every point.
+// The launch is a programmatic dependent launch (pe_common.cuh): shared-memory set-up, TMEM allocation and barrier initialisation run while
+// the operand-image kernel is still working; everything that reads its output sits behind pe_grid_dep_wait().
 // Reference lines: see pe_simt.cu / pe_device.cuh (the epilogue algebra is shared with the SIMT engine).
 #include <cuda_fp16.h>
 #include <cstdlib>
