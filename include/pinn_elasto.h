@@ -170,7 +170,11 @@ int pe_reduce_adam(const pe_plan *plan, const float *d_grad_partials, const floa
 
 /* Forward-only fields for `predict` (plate:561-570; semi:348-358): d_out[n][8] =
  * (u, v, s11, s22, s12, e11, e22, e12); formulation PE_RES_F5 or PE_RES_F7 selects the output columns
- * (F7 nets return cols 0,1,4,5,6).  Composite as in pe_term_desc (aux_k = 4 streams: value,x,y,t). */
+ * (F7 nets return cols 0,1,4,5,6).  Composite as in pe_term_desc (aux_k = 4 streams: value,x,y,t).
+ * Batches of >= 512 points of networks the tensor-core engine supports (hidden widths <= 56, at least two hidden
+ * layers) run its forward sweep (operand-image kernel + resid_tcf_kernel<4, FWD>; the images live in a buffer the plan
+ * allocates at the first such call, so one plan must not be used from two streams at once); everything else, and
+ * everything under PE_FIELDS_ENGINE=simt, runs the fp32 SIMT fields kernel.  Both meet the fields bar (2e-5). */
 int pe_forward_fields(const pe_plan *plan, int formulation, const float *d_points, int ld, int n,
                       const float *in_scale, const float *in_shift, const float *d_aux, int aux_k,
                       const float *d_params, float *d_out, void *stream);
