@@ -2,7 +2,7 @@
 families of the kernel -- forward layer GEMMs, adjoint GEMMs, weight-gradient GEMMs -- run on split-operand tensor-core arithmetic,
 everything else in float32, against the float64 jet oracle (oracle/jet_numpy.py).
 
-    python tests/emulate_engine_precision.py [n_points]      -> table on stdout (profiles/r1_engine_precision_study.txt)
+    python tests/emulate_engine_precision.py [n_points] [DEPTHxWIDTH, default 5x50]      -> table on stdout (profiles/r*_engine_precision_study*.txt)
 
 Schemes:
   fp32      : float32 GEMMs (what the SIMT engine does)
@@ -223,12 +223,13 @@ def block_err(g, gref, layers):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    depth, width = (int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else '5x50').split('x'))      # e.g. 8x70: the reference's shipped plate net
     rng = np.random.default_rng(1111)
     P = rng.uniform([0, 0, 0], [.5, .5, 10], (2 * n, 3))
     X = P[np.hypot(P[:, 0], P[:, 1]) > 0.1][:n]            # the bench workload's point distribution
-    layers = [3] + 5 * [50] + [5]
+    layers = [3] + depth * [width] + [5]
     Ws, bs = R.xavier_params(layers, seed=1111)
-    print('F5 collocation term, 5x50 net, %d points of the bench distribution; errors against the float64 jet oracle' % X.shape[0])
+    print('F5 collocation term, %dx%d net, %d points of the bench distribution; errors against the float64 jet oracle' % (depth, width, X.shape[0]))
     print('%-28s %12s %12s %16s' % ('scheme', 'loss_f_uv', 'loss_f_s', 'grad (block max)'))
     for label, Wl, bl in (('Xavier init', Ws, bs), ('Xavier x 1.5, biases 0.1', [w * 1.5 for w in Ws], [b + 0.1 for b in bs])):
         luv, ls, dW, db = J.loss_grad_residual('f5', X, Wl, bl, 10.0, 10.0, 20.0, 0.25, 1.0)
